@@ -1,0 +1,319 @@
+// Stereo warp + pad + SBS/TAB pack + Half-mode 2:1 mean + clamp — ONE kernel, HBM-bound, no tensor cores.
+//
+// Replaces make_sbs_core (reference depth.py:2122-2184), pad_to_aspect_tensor (:2106-2119), the
+// HWC/float conversion of chw_tensor_to_numpy (:767-773) and, when the depth map is passed at model
+// resolution, the final bilinear upsample of predict_depth (:1998-2004).
+//
+// Arithmetic contract (bit-exact against oracle/warp_oracle.c, which is pinned bit-exactly on the
+// reference's CPU output): strict fp32, compiled with -fmad=false; every FMA below is explicit and sits
+// exactly where ATen's linspace / grid_sampler_2d kernels contract one.
+//
+// Work decomposition: one thread produces 4 consecutive OUTPUT pixels of one output row.  The reference
+// materialises shifts, two [h,w,2] fp32 grids, two eye images, the concatenation and the pooled copy
+// (~10x the algorithmic bytes); here each source byte is read from HBM once and each
+// output byte written once.
+#include "common.cuh"
+
+namespace d2s {
+
+struct WarpK {
+    const void *rgb; long long rsc, rsy, rsx;
+    void *out; long long osc, osy, osx;
+    const void *depth; int dh, dw; float dscale_h, dscale_w;
+    int h, w, ph, pw, top, left, oh, ow;
+    int tab, half, gather, lowres, rgb_round;
+    float conv, ratio, max_px, strength, two_over_wm1;
+    float xstep; int xhalf; float ystep; int yhalf;
+    int *idx_l, *idx_r;
+};
+
+// torch.linspace(-1, 1, n)[i]  (RangeFactories: two-sided, one FMA per element)
+__device__ __forceinline__ float linspace_pm1(int i, int n, float step, int half) {
+    if (n == 1) return -1.0f;
+    return (i < half) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(n - i - 1), 1.0f);
+}
+
+// grid_sampler_compute_source_index, padding_mode=reflection, align_corners=True (GridSampler.cuh)
+__device__ __forceinline__ float source_index(float coord, int size) {
+    coord = __fmul_rn(__fmul_rn(__fadd_rn(coord, 1.f), 0.5f), (float)(size - 1));
+    if (size == 1) return 0.f;
+    const float span = (float)(size - 1);
+    float in = fabsf(coord);
+    if (in >= span) {  // rare: only within |shift| of the right border.  fmod/floor/div are exact here.
+        float extra = fmodf(in, span);
+        int flips = (int)floorf(__fdiv_rn(in, span));
+        in = (flips % 2 == 0) ? extra : __fsub_rn(span, extra);
+    }
+    // in < span: fmod(in,span)==in and floor(in/span)==0 exactly, so reflect_coordinates returns `in`.
+    return fminf(span, fmaxf(in, 0.f));
+}
+
+struct RowCtx {
+    int iy0;
+    float wy0, wy1;  // (iy_se - iy), (iy - iy_nw)
+    bool ok0, ok1;
+};
+
+__device__ __forceinline__ RowCtx make_row(const WarpK &k, int y) {
+    RowCtx r;
+    float iy = source_index(linspace_pm1(y, k.h, k.ystep, k.yhalf), k.h);
+    r.iy0 = (int)floorf(iy);
+    r.wy0 = __fsub_rn((float)(r.iy0 + 1), iy);
+    r.wy1 = __fsub_rn(iy, (float)r.iy0);
+    r.ok0 = r.iy0 >= 0 && r.iy0 < k.h;
+    r.ok1 = r.iy0 + 1 < k.h;
+    return r;
+}
+
+// depth at full-res pixel (y,x) in the value set of DT.  lowres: upsample_bilinear2d (align_corners=False),
+// restated from ATen's CUDA kernel (UpSampleBilinear2d.cu): accumulate in fp32, round to DT.
+template <typename DT>
+__device__ __forceinline__ float load_depth(const WarpK &k, int y, int x) {
+    const DT *d = (const DT *)k.depth;
+    if (!k.lowres) return to_f32<DT>(__ldg(d + (size_t)y * k.w + x));
+    float h1r = fmaxf(__fmaf_rn(k.dscale_h, (float)y + 0.5f, -0.5f), 0.f);
+    float w1r = fmaxf(__fmaf_rn(k.dscale_w, (float)x + 0.5f, -0.5f), 0.f);
+    int h1 = (int)h1r, w1 = (int)w1r;
+    int h1p = (h1 < k.dh - 1) ? 1 : 0, w1p = (w1 < k.dw - 1) ? 1 : 0;
+    float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
+    float w1l = __fsub_rn(w1r, (float)w1), w0l = __fsub_rn(1.f, w1l);
+    const DT *r0 = d + (size_t)h1 * k.dw, *r1 = d + (size_t)(h1 + h1p) * k.dw;
+    float a = to_f32<DT>(__ldg(r0 + w1)), b = to_f32<DT>(__ldg(r0 + w1 + w1p));
+    float c = to_f32<DT>(__ldg(r1 + w1)), e = to_f32<DT>(__ldg(r1 + w1 + w1p));
+    float top = __fmaf_rn(w0l, a, __fmul_rn(w1l, b));
+    float bot = __fmaf_rn(w0l, c, __fmul_rn(w1l, e));
+    return round_to<DT>(__fmaf_rn(h0l, top, __fmul_rn(h1l, bot)));
+}
+
+template <typename RT, typename DT>
+__device__ __forceinline__ float load_rgb(const WarpK &k, int c, int y, int x) {
+    float v = to_f32<RT>(__ldg((const RT *)k.rgb + c * k.rsc + (long long)y * k.rsy + (long long)x * k.rsx));
+    if (sizeof(RT) != 1 && k.rgb_round) v = round_to<DT>(v);  // rgb.to(depth.dtype), depth.py:2209-2215
+    if (sizeof(RT) != 1) v = fminf(fmaxf(v, 0.f), 255.f);  // img.clamp(0,255), depth.py:2142 (no-op for u8)
+    return v;
+}
+
+// One warped eye pixel.  e: 0 left, 1 right.
+template <typename RT, typename DT>
+__device__ __forceinline__ void eye_pixel(const WarpK &k, const RowCtx &row, int e, int y, int x, float rgb[3]) {
+    // shift chain, depth.py:2143-2147 (+ :2154): each tensor-scalar op is fp32 math rounded to DT
+    float d = round_to<DT>(__fsub_rn(load_depth<DT>(k, y, x), k.conv));
+    float inv = round_to<DT>(__fmul_rn(-d, k.ratio));
+    float s = round_to<DT>(__fmul_rn(inv, k.max_px));
+    s = round_to<DT>(__fmul_rn(s, k.strength));
+    int *idx = e ? k.idx_r : k.idx_l;
+    if (k.gather) {
+        // depth.py:2163-2172
+        float c = e ? __fsub_rn((float)x, s) : __fadd_rn((float)x, s);
+        int ci = (int)fminf(fmaxf(c, 0.f), (float)(k.w - 1));
+        if (idx) idx[(size_t)y * k.w + x] = ci;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) rgb[ch] = load_rgb<RT, DT>(k, ch, y, ci);
+        return;
+    }
+    // depth.py:2152-2160
+    float sn = round_to<DT>(__fmul_rn(s, k.two_over_wm1));
+    float xs = linspace_pm1(x, k.w, k.xstep, k.xhalf);
+    float gx = e ? __fsub_rn(xs, sn) : __fadd_rn(xs, sn);
+    float ix = source_index(gx, k.w);
+    int ix0 = (int)floorf(ix);
+    if (idx) idx[(size_t)y * k.w + x] = ix0;
+    float wx0 = __fsub_rn((float)(ix0 + 1), ix), wx1 = __fsub_rn(ix, (float)ix0);
+    float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
+    float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
+    bool okx1 = ix0 + 1 < k.w;  // ix0 in [0,w-1] after the clip
+    // A tap whose weight is exactly 0 contributes fma(v,0,acc)==acc: skipping its load is bit-identical.
+    bool t_nw = row.ok0, t_ne = row.ok0 && okx1 && ne != 0.f;
+    bool t_sw = row.ok1 && sw != 0.f, t_se = row.ok1 && okx1 && se != 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float acc = 0.f;
+        if (t_nw) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, row.iy0, ix0), nw, acc);
+        if (t_ne) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, row.iy0, ix0 + 1), ne, acc);
+        if (t_sw) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, row.iy0 + 1, ix0), sw, acc);
+        if (t_se) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, row.iy0 + 1, ix0 + 1), se, acc);
+        rgb[ch] = acc;
+    }
+}
+
+// element (cy,cx) of cat([pad(left), pad(right)]) — depth.py:2175-2181
+template <typename RT, typename DT>
+__device__ __forceinline__ void cat_pixel(const WarpK &k, const RowCtx *rows, int cy, int cx, float rgb[3]) {
+    int e, ey, ex;
+    if (k.tab) { e = cy >= k.ph; ey = cy - e * k.ph; ex = cx; }
+    else       { e = cx >= k.pw; ex = cx - e * k.pw; ey = cy; }
+    ey -= k.top; ex -= k.left;
+    if (ey < 0 || ey >= k.h || ex < 0 || ex >= k.w) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
+    // rows[] caches the per-row y interpolation context (warp-uniform): slot = which of the thread's rows
+    const RowCtx &row = rows[(k.half && k.tab) ? (cy & 1) : 0];
+    eye_pixel<RT, DT>(k, row, e, ey, ex, rgb);
+}
+
+// 4 pixels x 3 channels -> memory (vectorised when the layout allows)
+template <typename OT>
+__device__ __forceinline__ void store_px4(const WarpK &k, int oy, int ox, int n, const float (*v)[3]) {
+    OT *base = (OT *)k.out + (long long)oy * k.osy + (long long)ox * k.osx;
+    constexpr int kVecBytes = 4 * sizeof(OT);  // 4 elements: 16 B (f32), 8 B (f16), 4 B (u8)
+    if (n == 4 && k.osx == 3 && k.osc == 1 && ((uintptr_t)base % kVecBytes) == 0) {
+        // HWC: 12 contiguous elements
+        OT tmp[12];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tmp[p * 3 + c] = from_f32<OT>(v[p][c]);
+        if (sizeof(OT) == 4) { float4 *d = (float4 *)base; const float4 *s = (const float4 *)tmp; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+        else if (sizeof(OT) == 2) { uint2 *d = (uint2 *)base; const uint2 *s = (const uint2 *)tmp; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+        else { uint32_t *d = (uint32_t *)base; const uint32_t *s = (const uint32_t *)tmp; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+        return;
+    }
+    if (n == 4 && k.osx == 1 && ((uintptr_t)base % kVecBytes) == 0 && ((k.osc * (long long)sizeof(OT)) % kVecBytes) == 0) {
+        // CHW: 4 contiguous elements per plane
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            OT tmp[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) tmp[p] = from_f32<OT>(v[p][c]);
+            OT *d = base + c * k.osc;
+            if (sizeof(OT) == 4) *(float4 *)d = *(const float4 *)tmp;
+            else if (sizeof(OT) == 2) *(uint2 *)d = *(const uint2 *)tmp;
+            else *(uint32_t *)d = *(const uint32_t *)tmp;
+        }
+        return;
+    }
+    for (int p = 0; p < n; ++p)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) base[c * k.osc + p * k.osx] = from_f32<OT>(v[p][c]);
+}
+
+template <typename RT, typename DT, typename OT>
+__global__ void __launch_bounds__(256) warp_sbs_kernel(const WarpK k) {
+    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (oy >= k.oh || ox0 >= k.ow) return;
+    const int n = min(4, k.ow - ox0);
+
+    // y-interpolation context for the (one or two) eye rows this thread touches
+    RowCtx rows[2];
+    {
+        int cy0 = (k.half && k.tab) ? 2 * oy : oy;
+        int ey0 = (k.tab ? (cy0 >= k.ph ? cy0 - k.ph : cy0) : cy0) - k.top;
+        // Half-TAB pairs (2oy, 2oy+1) never straddle the eye seam unless ph is odd; rows[] is indexed by
+        // (cy & 1), so slot 0 holds the even cat row and slot 1 the odd one.
+        int cy1 = cy0 + 1;
+        int ey1 = (k.tab ? (cy1 >= k.ph ? cy1 - k.ph : cy1) : cy1) - k.top;
+        rows[0] = make_row(k, min(max(ey0, 0), k.h - 1));
+        rows[1] = (k.half && k.tab) ? make_row(k, min(max(ey1, 0), k.h - 1)) : rows[0];
+    }
+
+    float v[4][3];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (p >= n) { v[p][0] = v[p][1] = v[p][2] = 0.f; continue; }
+        const int ox = ox0 + p;
+        float a[3];
+        if (!k.half) {
+            cat_pixel<RT, DT>(k, rows, oy, ox, a);
+        } else {
+            // F.interpolate(mode="area") with an exact 2:1 ratio == adaptive_avg_pool: (a + b) / 2
+            float b[3];
+            if (k.tab) { cat_pixel<RT, DT>(k, rows, 2 * oy, ox, a); cat_pixel<RT, DT>(k, rows, 2 * oy + 1, ox, b); }
+            else       { cat_pixel<RT, DT>(k, rows, oy, 2 * ox, a); cat_pixel<RT, DT>(k, rows, oy, 2 * ox + 1, b); }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a[c] = __fmul_rn(__fadd_rn(a[c], b[c]), 0.5f);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[p][c] = fminf(fmaxf(a[c], 0.f), 255.f);  // final clamp, depth.py:2184
+    }
+    store_px4<OT>(k, oy, ox0, n, v);
+}
+
+static void pad_geometry(int h, int w, int fill, int *ph, int *pw, int *top, int *left) {
+    // depth.py:2106-2119 (python float == double)
+    *ph = h; *pw = w; *top = 0; *left = 0;
+    if (!fill) return;
+    double r_img = (double)w / (double)h, r_t = 16.0 / 9.0;
+    if (fabs(r_img - r_t) < 1e-3) return;
+    if (r_img > r_t) { int nh = (int)nearbyint((double)w / r_t); *ph = nh; *top = (nh - h) / 2; }
+    else             { int nw = (int)nearbyint((double)h * r_t); *pw = nw; *left = (nw - w) / 2; }
+}
+
+template <typename RT, typename DT>
+static int launch_out(const WarpK &k, int out_dtype, dim3 grid, dim3 block, d2s_stream_t st) {
+    switch (out_dtype) {
+        case D2S_F32: D2S_LAUNCH((warp_sbs_kernel<RT, DT, float>), grid, block, 0, st, k); break;
+        case D2S_F16: D2S_LAUNCH((warp_sbs_kernel<RT, DT, __half>), grid, block, 0, st, k); break;
+        case D2S_U8:  D2S_LAUNCH((warp_sbs_kernel<RT, DT, uint8_t>), grid, block, 0, st, k); break;
+        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs: out dtype %d unsupported", out_dtype);
+    }
+    return D2S_OK;
+}
+template <typename RT>
+static int launch_depth(const WarpK &k, int depth_dtype, int out_dtype, dim3 grid, dim3 block, d2s_stream_t st) {
+    switch (depth_dtype) {
+        case D2S_F32: return launch_out<RT, float>(k, out_dtype, grid, block, st);
+        case D2S_F16: return launch_out<RT, __half>(k, out_dtype, grid, block, st);
+        case D2S_BF16: return launch_out<RT, __nv_bfloat16>(k, out_dtype, grid, block, st);
+        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs: depth dtype %d unsupported", depth_dtype);
+    }
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_sbs_out_shape(int h, int w, int display_mode, int fill_16_9, int *out_h, int *out_w) {
+    D2S_REQUIRE(h > 0 && w > 0 && out_h && out_w, "d2s_sbs_out_shape: bad arguments");
+    D2S_REQUIRE(display_mode >= 0 && display_mode <= 3, "d2s_sbs_out_shape: display_mode %d", display_mode);
+    int ph, pw, t, l;
+    pad_geometry(h, w, fill_16_9, &ph, &pw, &t, &l);
+    bool tab = display_mode == D2S_FULL_TAB || display_mode == D2S_HALF_TAB;
+    bool half = display_mode == D2S_HALF_SBS || display_mode == D2S_HALF_TAB;
+    *out_h = half ? ph : (tab ? 2 * ph : ph);
+    *out_w = half ? pw : (tab ? pw : 2 * pw);
+    return D2S_OK;
+}
+
+extern "C" int d2s_make_sbs(const d2s_warp_params *p, d2s_stream_t stream) {
+    D2S_REQUIRE(p != nullptr, "d2s_make_sbs: null params");
+    D2S_REQUIRE(p->rgb.base && p->out.base && p->depth, "d2s_make_sbs: null buffer");
+    D2S_REQUIRE(p->h >= 1 && p->w >= 2, "d2s_make_sbs: eye size %dx%d unsupported (need w >= 2)", p->h, p->w);
+    D2S_REQUIRE(p->display_mode >= 0 && p->display_mode <= 3, "d2s_make_sbs: display_mode %d", p->display_mode);
+    D2S_REQUIRE(p->warp_mode == D2S_WARP_BILINEAR || p->warp_mode == D2S_WARP_GATHER, "d2s_make_sbs: warp_mode %d", p->warp_mode);
+    D2S_REQUIRE(p->depth_h >= 1 && p->depth_w >= 1, "d2s_make_sbs: depth size %dx%d", p->depth_h, p->depth_w);
+    WarpK k{};
+    k.rgb = p->rgb.base; k.rsc = p->rgb.sc; k.rsy = p->rgb.sy; k.rsx = p->rgb.sx;
+    k.out = p->out.base; k.osc = p->out.sc; k.osy = p->out.sy; k.osx = p->out.sx;
+    k.depth = p->depth; k.dh = p->depth_h; k.dw = p->depth_w;
+    k.lowres = !(p->depth_h == p->h && p->depth_w == p->w);
+    k.dscale_h = (float)p->depth_h / (float)p->h;   // area_pixel_compute_scale, align_corners=False
+    k.dscale_w = (float)p->depth_w / (float)p->w;
+    k.h = p->h; k.w = p->w;
+    pad_geometry(p->h, p->w, p->fill_16_9, &k.ph, &k.pw, &k.top, &k.left);
+    k.tab = p->display_mode == D2S_FULL_TAB || p->display_mode == D2S_HALF_TAB;
+    k.half = p->display_mode == D2S_HALF_SBS || p->display_mode == D2S_HALF_TAB;
+    k.oh = k.half ? k.ph : (k.tab ? 2 * k.ph : k.ph);
+    k.ow = k.half ? k.pw : (k.tab ? k.pw : 2 * k.pw);
+    k.gather = p->warp_mode == D2S_WARP_GATHER;
+    k.rgb_round = p->rgb_round_to_depth_dtype != 0;
+    k.conv = p->convergence; k.ratio = p->depth_ratio;
+    k.max_px = (float)((double)p->ipd_uv * (double)p->w);  // python: ipd_uv * W (double), then fp32 scalar
+    k.strength = (float)0.05;
+    k.two_over_wm1 = (float)(2.0 / (double)(p->w - 1));
+    k.xstep = 2.0f / (float)(p->w - 1); k.xhalf = p->w / 2;
+    k.ystep = p->h > 1 ? 2.0f / (float)(p->h - 1) : 0.f; k.yhalf = p->h / 2;
+    k.idx_l = p->idx_left; k.idx_r = p->idx_right;
+
+    dim3 block(128, 2);
+    dim3 grid(ceil_div(ceil_div(k.ow, 4), block.x), ceil_div(k.oh, block.y));
+    int rc;
+    switch (p->rgb.dtype) {
+        case D2S_U8:  rc = launch_depth<uint8_t>(k, p->depth_dtype, p->out.dtype, grid, block, stream); break;
+        case D2S_F16: rc = launch_depth<__half>(k, p->depth_dtype, p->out.dtype, grid, block, stream); break;
+        case D2S_F32: rc = launch_depth<float>(k, p->depth_dtype, p->out.dtype, grid, block, stream); break;
+        case D2S_BF16: rc = launch_depth<__nv_bfloat16>(k, p->depth_dtype, p->out.dtype, grid, block, stream); break;
+        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs: rgb dtype %d unsupported", p->rgb.dtype);
+    }
+    if (rc != D2S_OK) return rc;
+    D2S_POST_LAUNCH();
+    return D2S_OK;
+}

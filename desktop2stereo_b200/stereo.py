@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's stereo functions, backed by libd2s_b200's warp kernel.
+
+Same names, argument meaning and defaults as the reference:
+    make_sbs_core   depth.py:2122-2184
+    make_sbs        depth.py:2186-2231
+PyTorch appears only as the owner of device memory and of the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DISPLAY_MODES, Image, WarpParams
+
+_TORCH2D2S = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.uint8: _lib.U8}
+_D2S2TORCH = {v: k for k, v in _TORCH2D2S.items()}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.D2SError(f"{what} must live on a CUDA device (got {t.device}); there is no CPU path")
+
+
+def image_view(t: torch.Tensor, layout: str) -> Image:
+    """Describe a torch tensor as a d2s_image.  layout: 'CHW' [3,h,w], 'HWC' [h,w,3] (RGB) or
+    'BGRA'/'BGR' [h,w,4|3] (capture order, read as RGB through a negative channel stride)."""
+    es = t.element_size()
+    img = Image()
+    img.dtype = _TORCH2D2S[t.dtype]
+    if layout == "CHW":
+        assert t.dim() == 3 and t.shape[0] >= 3
+        img.base, img.sc, img.sy, img.sx = t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
+    elif layout == "HWC":
+        assert t.dim() == 3 and t.shape[2] >= 3
+        img.base, img.sc, img.sy, img.sx = t.data_ptr(), t.stride(2), t.stride(0), t.stride(1)
+    elif layout in ("BGRA", "BGR"):
+        assert t.dim() == 3 and t.shape[2] >= 3
+        img.base = t.data_ptr() + 2 * t.stride(2) * es
+        img.sc, img.sy, img.sx = -t.stride(2), t.stride(0), t.stride(1)
+    else:
+        raise ValueError(layout)
+    return img
+
+
+def sbs_out_shape(h: int, w: int, display_mode: str = "Half-SBS", fill_16_9: bool = False):
+    oh, ow = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().d2s_sbs_out_shape(h, w, DISPLAY_MODES[display_mode], int(fill_16_9),
+                                            C.byref(oh), C.byref(ow)), "d2s_sbs_out_shape")
+    return oh.value, ow.value
+
+
+def make_sbs_core(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ratio=2.0,
+                  display_mode="Half-SBS", fill_16_9=False, convergence=0.0, device=None, *,
+                  rgb_layout="CHW", out: torch.Tensor | None = None, out_dtype=None, out_layout="CHW",
+                  gather=False, return_indices=False, round_rgb_to_depth_dtype=False):
+    """depth.py:2122-2184.  rgb [3,h,w] (0..255), depth [h,w] in [0,1] (or a lower-resolution map,
+    which is bilinearly upsampled inside the kernel exactly as depth.py:1998-2004 would).  Returns the
+    packed stereo image [3,oh,ow] (or [oh,ow,3] with out_layout='HWC'), fp32 like the reference's
+    grid_sample branch unless out_dtype says otherwise."""
+    _require_cuda(rgb, "rgb"), _require_cuda(depth, "depth")
+    if display_mode not in DISPLAY_MODES:
+        raise ValueError(f"display_mode {display_mode!r}")
+    if rgb_layout == "CHW":
+        h, w = rgb.shape[1:]
+    else:
+        h, w = rgb.shape[:2]
+    if depth.dim() != 2:
+        depth = depth.squeeze()
+    depth = depth.contiguous()
+    oh, ow = sbs_out_shape(h, w, display_mode, fill_16_9)
+    if out is None:
+        if out_dtype is None:
+            out_dtype = depth.dtype if gather else torch.float32
+        shape = (3, oh, ow) if out_layout == "CHW" else (oh, ow, 3)
+        out = torch.empty(shape, dtype=out_dtype, device=rgb.device)
+    p = WarpParams()
+    p.rgb = image_view(rgb, rgb_layout)
+    p.out = image_view(out, out_layout)
+    p.depth, p.depth_dtype = depth.data_ptr(), _TORCH2D2S[depth.dtype]
+    p.depth_h, p.depth_w, p.h, p.w = depth.shape[0], depth.shape[1], h, w
+    p.ipd_uv, p.depth_ratio, p.convergence = float(ipd_uv), float(depth_ratio), float(convergence)
+    p.display_mode, p.fill_16_9 = DISPLAY_MODES[display_mode], int(bool(fill_16_9))
+    p.warp_mode = _lib.WARP_GATHER if gather else _lib.WARP_BILINEAR
+    p.rgb_round_to_depth_dtype = int(bool(round_rgb_to_depth_dtype))
+    il = ir = None
+    if return_indices:
+        il = torch.empty((h, w), dtype=torch.int32, device=rgb.device)
+        ir = torch.empty((h, w), dtype=torch.int32, device=rgb.device)
+        p.idx_left, p.idx_right = il.data_ptr(), ir.data_ptr()
+    with torch.cuda.device(rgb.device):
+        _lib.check(_lib.lib().d2s_make_sbs(C.byref(p), _stream_ptr(rgb.device)), "d2s_make_sbs")
+    return (out, il, ir) if return_indices else out
+
+
+class _PinnedRing:
+    """Ring of pinned host buffers for the float32 HWC result of make_sbs (depth.py:767-773).
+    A frame handed out stays valid for `depth-1` further calls."""
+
+    def __init__(self, depth=4):
+        self.depth, self.bufs, self.i = depth, {}, 0
+
+    def get(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        ring = self.bufs.get(key)
+        if ring is None:
+            ring = self.bufs[key] = [torch.empty(shape, dtype=dtype, pin_memory=True) for _ in range(self.depth)]
+        self.i = (self.i + 1) % self.depth
+        return ring[self.i]
+
+
+_ring = _PinnedRing()
+_default_device = None
+
+
+def default_device():
+    global _default_device
+    if _default_device is None:
+        if not torch.cuda.is_available():
+            raise _lib.D2SError("no CUDA device: desktop2stereo_b200 has no CPU path")
+        _default_device = torch.device("cuda", torch.cuda.current_device())
+    return _default_device
+
+
+def make_sbs(rgb_c, depth, ipd_uv=0.064, depth_ratio=2.0, convergence=0.0, fill_16_9=False,
+             display_mode="Half-SBS", fps=None, *, out_dtype=torch.float32):
+    """depth.py:2186-2231.  rgb_c: np.ndarray [h,w,3] (RGB) or torch.Tensor [3,h,w]; depth: tensor or
+    ndarray [h,w].  Returns the host float32 HWC frame the reference returns (`out_dtype=torch.uint8`
+    gives the 12x smaller u8 frame instead)."""
+    if isinstance(depth, np.ndarray):
+        depth = torch.from_numpy(depth)
+    dev = depth.device if depth.is_cuda else default_device()
+    depth = depth.to(dev, non_blocking=True)
+    if isinstance(rgb_c, np.ndarray):
+        rgb = torch.from_numpy(rgb_c).to(dev, non_blocking=True)
+        layout = "HWC" if (rgb.dim() == 3 and rgb.shape[2] == 3) else "CHW"
+    else:
+        rgb, layout = rgb_c.to(dev, non_blocking=True), "CHW"
+    if fps is not None:
+        from .overlay import overlay_fps
+        rgb = overlay_fps(rgb, fps, layout=layout)
+    # the reference casts rgb to depth.dtype before the warp (depth.py:2209-2215)
+    round_rgb = rgb.dtype.is_floating_point and rgb.dtype != depth.dtype
+    sbs = make_sbs_core(rgb, depth, ipd_uv=ipd_uv, depth_ratio=depth_ratio, display_mode=display_mode,
+                        fill_16_9=fill_16_9, convergence=convergence, rgb_layout=layout,
+                        out_dtype=out_dtype, out_layout="HWC", round_rgb_to_depth_dtype=round_rgb)
+    host = _ring.get(sbs.shape, sbs.dtype)
+    host.copy_(sbs, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return host.numpy()

@@ -1,0 +1,165 @@
+/* d2s_b200 — C ABI of the B200-native depth-inference + stereo-warp hot path.
+ *
+ * Drop-in boundary for lc700x/desktop2stereo's `depth.py` hot path.  Every entry
+ * point takes plain pointers/sizes (device pointers unless stated), enqueues on the caller's
+ * stream, never host-synchronises, never allocates caller-visible memory, and returns 0 on
+ * success or a non-zero status with a message retrievable through d2s_last_error() — the same
+ * convention as the reference's own ctypes→cudart wrapper (reference viewer.py:20-146, rc != 0
+ * -> RuntimeError at viewer.py:104-105).
+ *
+ * Which reference interface each entry point replaces:
+ *   d2s_make_sbs        depth.py:2122-2184 make_sbs_core (+ pad_to_aspect_tensor :2106-2119,
+ *                       the HWC/float conversion of chw_tensor_to_numpy :767-773, and optionally
+ *                       the depth upsample of predict_depth :1998-2004 fused into the gather)
+ *   d2s_process         depth.py:542-566  process() CUDA branch (BGRA/BGR u8 HWC -> RGB CHW)
+ *   d2s_preprocess      depth.py:676-706 _resize_patch_aligned_t (bicubic+antialias) fused with
+ *                       the /255 and mean/std normalisation of predict_depth :1931,1946-1948
+ *   d2s_create/_infer/_destroy
+ *                       the engine object assigned to DepthModelWrapper.model
+ *                       (depth.py:1763-1781; template: TensorRTEngine depth.py:1457-1536)
+ *   d2s_postprocess     depth.py:806-867 post_process_depth/normalize, :775 apply_gamma,
+ *                       :709-736 apply_foreground_scale, :740-765 anti_alias,
+ *                       :1865-1887 DepthStabilizer, :1998-2004 final bilinear upsample
+ *   d2s_overlay_fps     depth.py:2061-2103 overlay_fps
+ */
+#ifndef D2S_B200_H
+#define D2S_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *d2s_stream_t;            /* cudaStream_t */
+typedef struct d2s_engine *d2s_handle; /* opaque engine (packed weights + workspace), one per GPU */
+
+enum d2s_status {
+    D2S_OK = 0,
+    D2S_ERR_INVALID = 1,   /* bad argument */
+    D2S_ERR_CUDA = 2,      /* a CUDA runtime/driver call failed */
+    D2S_ERR_UNSUPPORTED = 3,
+    D2S_ERR_NOMEM = 4
+};
+
+enum d2s_dtype { D2S_F32 = 0, D2S_F16 = 1, D2S_BF16 = 2, D2S_U8 = 3 };
+enum d2s_display_mode { D2S_FULL_SBS = 0, D2S_HALF_SBS = 1, D2S_FULL_TAB = 2, D2S_HALF_TAB = 3 };
+enum d2s_warp_mode {
+    D2S_WARP_BILINEAR = 0, /* depth.py:2152-2160 grid_sample branch (CUDA path of the reference) */
+    D2S_WARP_GATHER = 1    /* depth.py:2163-2172 integer gather branch */
+};
+
+/* A strided 3-channel image view: element (c,y,x) lives at base[c*sc + y*sy + x*sx] (in elements).
+ * CHW planar RGB: sc=h*w, sy=w, sx=1.   HWC RGB: sc=1, sy=3*w, sx=3.
+ * HWC BGRA (capture format, depth.py:549): base=&px[2], sc=-1, sy=4*w, sx=4. */
+typedef struct d2s_image {
+    void *base;
+    int32_t dtype; /* enum d2s_dtype */
+    int32_t reserved;
+    int64_t sc, sy, sx;
+} d2s_image;
+
+typedef struct d2s_warp_params {
+    d2s_image rgb; /* source eye image, h x w, values 0..255 */
+    d2s_image out; /* packed stereo frame, out_h x out_w (see d2s_sbs_out_shape) */
+    const void *depth;   /* [depth_h, depth_w] contiguous, dtype depth_dtype, values in [0,1] */
+    int32_t depth_dtype; /* D2S_F32 / D2S_F16 / D2S_BF16: the shift chain rounds to this dtype (depth.py:2143-2147) */
+    int32_t depth_h, depth_w; /* == h,w: full-res depth.  Otherwise the bilinear align_corners=False
+                                 upsample of depth.py:1998-2004 is evaluated inside the gather. */
+    int32_t h, w;
+    float ipd_uv, depth_ratio, convergence;
+    int32_t display_mode; /* enum d2s_display_mode */
+    int32_t fill_16_9;
+    int32_t warp_mode;    /* enum d2s_warp_mode */
+    int32_t rgb_round_to_depth_dtype; /* 1: round rgb values to depth_dtype on load (make_sbs casts
+                                         rgb to depth.dtype, depth.py:2209-2215) */
+    int32_t *idx_left;    /* optional [h,w] int32 debug taps: floor(ix) or the gather coordinate */
+    int32_t *idx_right;
+} d2s_warp_params;
+
+/* Output geometry of make_sbs_core for an h x w eye (depth.py:2175-2183). */
+int d2s_sbs_out_shape(int h, int w, int display_mode, int fill_16_9, int *out_h, int *out_w);
+
+/* Stereo warp + pad + SBS/TAB pack + (Half modes) 2:1 area mean + clamp, one kernel. */
+int d2s_make_sbs(const d2s_warp_params *p, d2s_stream_t stream);
+
+/* process(): BGRA/BGR u8 HWC [h0,w0,ch] -> RGB CHW [3,h,w] of out_dtype (F16/F32).  If (h,w) ==
+ * (h0,w0) it is a pure swizzle+cast, else the bilinear+antialias downscale of depth.py:560-566. */
+int d2s_process(const uint8_t *frame, int h0, int w0, int channels, void *out, int out_dtype, int h, int w,
+                d2s_stream_t stream);
+
+/* Patch-aligned model-input size of depth.py:676-692 for an h x w frame. */
+int d2s_model_input_shape(int h, int w, int target, int patch, int *new_h, int *new_w);
+
+/* _resize_patch_aligned_t (bicubic, antialias, align_corners=False) + /255 + (x-mean)/std.
+ * src: RGB image view (any layout/dtype of d2s_image), dst: [3,new_h,new_w] CHW of dst_dtype. */
+int d2s_preprocess(const d2s_image *src, int h, int w, void *dst, int dst_dtype, int new_h, int new_w,
+                   const float mean[3], const float std[3], void *workspace, size_t workspace_bytes,
+                   d2s_stream_t stream);
+size_t d2s_preprocess_workspace_bytes(int h, int w, int new_h, int new_w);
+
+/* ---- depth network (DINOv2 ViT encoder + DPT head) ---- */
+typedef struct d2s_model_config {
+    int32_t hidden;      /* D: 384 / 768 / 1024 */
+    int32_t layers;      /* L: 12 / 12 / 24 */
+    int32_t heads;       /* 6 / 12 / 16 (head dim must be 64) */
+    int32_t mlp_hidden;  /* 4*D */
+    int32_t patch;       /* 14 */
+    int32_t pos_grid;    /* 37 (pos-embed table is pos_grid^2 + 1 rows) */
+    int32_t out_indices[4]; /* 1-based hidden-state indices, e.g. {3,6,9,12} */
+    int32_t neck[4];     /* neck_hidden_sizes */
+    int32_t fusion;      /* fusion_hidden_size */
+    int32_t head_hidden; /* 32 */
+    float layer_norm_eps;
+    float max_depth;     /* 1.0 for relative models */
+    int32_t metric;      /* 0: final ReLU, 1: final sigmoid*max_depth */
+    int32_t max_batch;   /* workspace is sized for this many frames per call */
+    int32_t max_h, max_w;/* largest model input (multiples of patch) */
+} d2s_model_config;
+
+/* weight_blob: host pointer to the packed fp32 parameter blob produced by
+ * desktop2stereo_b200.weights.pack_state_dict (layout documented there and in DESIGN.md). */
+int d2s_create(const void *weight_blob, size_t nbytes, const d2s_model_config *cfg, int device, d2s_handle *out);
+int d2s_destroy(d2s_handle h);
+/* pixel_values [B,3,H,W] (F16 or F32, normalised) -> predicted_depth [B,H,W] (F16 or F32). */
+int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, void *depth_out, int out_dtype,
+              int B, int H, int W, d2s_stream_t stream);
+/* Debug/parity taps: copy an internal activation (by name) to a caller buffer as fp32. */
+int d2s_debug_tap(d2s_handle h, const char *name, float *dst, size_t max_elems, size_t *n_elems, d2s_stream_t stream);
+size_t d2s_workspace_bytes(d2s_handle h);
+int64_t d2s_launch_count(void); /* kernels launched by this library since load (for gpu_launches) */
+
+/* ---- depth post-process ---- */
+typedef struct d2s_post_params {
+    const void *depth_in; /* [H,W] raw predicted_depth */
+    int32_t in_dtype;
+    int32_t H, W;
+    void *out;            /* [out_h,out_w], dtype out_dtype: post-processed (+EMA) depth, upsampled */
+    int32_t out_dtype;
+    int32_t out_h, out_w; /* == H,W: no upsample */
+    int32_t compute_dtype; /* dtype the reference would compute in (F16 on CUDA, BF16 on CPU, F32) */
+    int32_t metric;       /* 1: 1/d on d>0 before the percentile clip */
+    float percentile;     /* 2.0 */
+    int32_t subsample_cap;/* 6144 */
+    float gamma;          /* 1.45 */
+    float foreground_scale; /* settings/10 */
+    float aa_strength;    /* settings*2 */
+    void *ema_state;      /* optional [H,W] compute_dtype persistent buffer (DepthStabilizer.prev) */
+    int32_t ema_valid;    /* 0: first frame (state := depth), 1: lerp */
+    float ema_alpha;      /* 0.9 */
+    void *workspace; size_t workspace_bytes;
+} d2s_post_params;
+size_t d2s_postprocess_workspace_bytes(int H, int W);
+int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream);
+
+/* overlay_fps: blends the "FPS: xx.x" glyph mask into an RGB image in place. */
+int d2s_overlay_fps(const d2s_image *rgb, int h, int w, const char *text, d2s_stream_t stream);
+
+const char *d2s_last_error(void);
+const char *d2s_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2S_B200_H */
