@@ -29,7 +29,7 @@ class Image(C.Structure):
 class WarpParams(C.Structure):
     _fields_ = [("rgb", Image), ("out", Image), ("depth", C.c_void_p), ("depth_dtype", C.c_int32),
                 ("depth_h", C.c_int32), ("depth_w", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("ipd_uv", C.c_float), ("depth_ratio", C.c_float), ("convergence", C.c_float),
+                ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
                 ("display_mode", C.c_int32), ("fill_16_9", C.c_int32), ("warp_mode", C.c_int32),
                 ("rgb_round_to_depth_dtype", C.c_int32),
                 ("idx_left", C.c_void_p), ("idx_right", C.c_void_p)]
@@ -49,7 +49,7 @@ class PostParams(C.Structure):
                 ("compute_dtype", C.c_int32), ("metric", C.c_int32), ("percentile", C.c_float),
                 ("subsample_cap", C.c_int32), ("gamma", C.c_float), ("foreground_scale", C.c_float),
                 ("aa_strength", C.c_float), ("ema_state", C.c_void_p), ("ema_valid", C.c_int32),
-                ("ema_alpha", C.c_float), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("ema_alpha", C.c_float), ("out_lowres", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 # every symbol include/d2s_b200.h declares: name -> (restype, argtypes)

@@ -1,0 +1,475 @@
+// Pre- and post-processing around the depth network (all HBM/latency-bound, no tensor cores).
+//
+//   d2s_process          depth.py:542-566   BGRA/BGR u8 HWC -> RGB CHW (+ optional bilinear-antialias downscale)
+//   d2s_preprocess       depth.py:676-706 + :1931 + :1946-1948   bicubic-antialias resize, /255, (x-mean)/std
+//   d2s_postprocess      depth.py:806-867 (+:775, :709-736, :740-765), :1865-1887 EMA, :1998-2004 upsample
+//
+// The separable antialias resampler follows ATen's upsample_gen2d_aa_out_frame (UpSampleBicubic2d.cu /
+// UpSample.cuh, torch 2.11): per-output span [xmin, xmin+xsize), filter evaluated at
+// (j + (xmin - center) + 0.5) * invscale, weights normalised by their sum, horizontal dot products first,
+// then the vertical one — evaluated in fp32.  Compiled with -fmad=false; FMAs are explicit.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace d2s {
+
+// ------------------------------------------------------------------------------------------------
+// antialias resampler
+// ------------------------------------------------------------------------------------------------
+struct AATable {  // per output index: span + normalised weights (K floats)
+    int *xmin;
+    int *xsize;
+    float *w;
+    int K;
+};
+
+__device__ __forceinline__ float bicubic_aa(float x) {  // BicubicFilterFunctor, a = -0.5
+    const float a = -0.5f;
+    if (x < 0) x = -x;
+    if (x < 1.f) return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(a + 2.f, x), a + 3.f), x), x), 1.f);
+    if (x < 2.f) return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(x, 5.f), x), 8.f), x), 4.f), a);
+    return 0.f;
+}
+__device__ __forceinline__ float bilinear_aa(float x) {  // BilinearFilterFunctor
+    if (x < 0) x = -x;
+    return x < 1.f ? __fsub_rn(1.f, x) : 0.f;
+}
+
+template <bool CUBIC>
+__global__ void aa_table_kernel(AATable t, int in_size, int out_size, float scale, float support) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= out_size) return;
+    float center = __fmul_rn(scale, (float)i + 0.5f);
+    int xmin = max((int)(__fadd_rn(__fsub_rn(center, support), 0.5f)), 0);
+    int xsize = min((int)(__fadd_rn(__fadd_rn(center, support), 0.5f)), in_size) - xmin;
+    xsize = min(max(xsize, 0), t.K);
+    float invscale = scale >= 1.f ? __fdiv_rn(1.f, scale) : 1.f;
+    float xmc = __fsub_rn((float)xmin, center);
+    float *w = t.w + (size_t)i * t.K;
+    float total = 0.f;
+    for (int j = 0; j < xsize; ++j) {
+        float x = __fmul_rn(__fadd_rn(__fadd_rn((float)j, xmc), 0.5f), invscale);
+        float v = CUBIC ? bicubic_aa(x) : bilinear_aa(x);
+        w[j] = v;
+        total = __fadd_rn(total, v);
+    }
+    for (int j = 0; j < xsize; ++j)
+        if (total != 0.f) w[j] = __fdiv_rn(w[j], total);
+    for (int j = xsize; j < t.K; ++j) w[j] = 0.f;
+    t.xmin[i] = xmin;
+    t.xsize[i] = xsize;
+}
+
+struct ImgView { const void *base; long long sc, sy, sx; };
+
+// horizontal pass: src (strided, ST) [3,h,w] -> tmp [3,h,ow] fp32
+template <typename ST>
+__global__ void aa_resize_h_kernel(ImgView src, int h, int ow, AATable t, float *__restrict__ tmp) {
+    int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (ox >= ow) return;
+    int xmin = t.xmin[ox], xsize = t.xsize[ox];
+    const float *w = t.w + (size_t)ox * t.K;
+    const ST *row = (const ST *)src.base + (long long)y * src.sy + (long long)xmin * src.sx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int j = 0; j < xsize; ++j) {
+        float wj = w[j];
+        const ST *p = row + (long long)j * src.sx;
+        float v0 = to_f32<ST>(__ldg(p)), v1 = to_f32<ST>(__ldg(p + src.sc)), v2 = to_f32<ST>(__ldg(p + 2 * src.sc));
+        if (j == 0) { a0 = __fmul_rn(v0, wj); a1 = __fmul_rn(v1, wj); a2 = __fmul_rn(v2, wj); }
+        else { a0 = __fmaf_rn(v0, wj, a0); a1 = __fmaf_rn(v1, wj, a1); a2 = __fmaf_rn(v2, wj, a2); }
+    }
+    size_t plane = (size_t)h * ow, o = (size_t)y * ow + ox;
+    tmp[o] = a0; tmp[plane + o] = a1; tmp[2 * plane + o] = a2;
+}
+
+// vertical pass + epilogue.  NORM: ((v/255) - mean)/std  (depth.py:1931, 1946-1948)
+template <typename OT, bool NORM>
+__global__ void aa_resize_v_kernel(const float *__restrict__ tmp, int h, int ow, int oh, AATable t, OT *__restrict__ dst,
+                                   float m0, float m1, float m2, float s0, float s1, float s2) {
+    int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    int oy = blockIdx.y, c = blockIdx.z;
+    if (ox >= ow) return;
+    int ymin = t.xmin[oy], ysize = t.xsize[oy];
+    const float *w = t.w + (size_t)oy * t.K;
+    const float *col = tmp + (size_t)c * h * ow + (size_t)ymin * ow + ox;
+    float acc = 0.f;
+    for (int j = 0; j < ysize; ++j) {
+        float v = col[(size_t)j * ow];
+        acc = (j == 0) ? __fmul_rn(v, w[0]) : __fmaf_rn(v, w[j], acc);
+    }
+    if (NORM) {
+        float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        acc = __fdiv_rn(__fsub_rn(__fdiv_rn(acc, 255.0f), mean), sd);
+    }
+    dst[(size_t)c * oh * ow + (size_t)oy * ow + ox] = from_f32<OT>(acc);
+}
+
+// no-resize fast path of process(): BGR(A) u8 HWC -> RGB CHW, 4 pixels per thread
+template <typename OT>
+__global__ void swizzle_chw_kernel(const uint8_t *__restrict__ src, int h, int w, int ch, OT *__restrict__ dst) {
+    long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    long long n = (long long)h * w;
+    if (i4 >= n) return;
+    float r[4], g[4], b[4];
+    int cnt = (int)min(4LL, n - i4);
+    if (ch == 4 && cnt == 4) {
+        uint4 q = __ldg((const uint4 *)(src + i4 * 4));
+        uint32_t px[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { b[p] = (float)(px[p] & 0xff); g[p] = (float)((px[p] >> 8) & 0xff); r[p] = (float)((px[p] >> 16) & 0xff); }
+    } else {
+        for (int p = 0; p < cnt; ++p) {
+            const uint8_t *q = src + (i4 + p) * ch;
+            b[p] = (float)q[0]; g[p] = (float)q[1]; r[p] = (float)q[2];
+        }
+    }
+    for (int p = 0; p < cnt; ++p) {
+        dst[i4 + p] = from_f32<OT>(r[p]);
+        dst[n + i4 + p] = from_f32<OT>(g[p]);
+        dst[2 * n + i4 + p] = from_f32<OT>(b[p]);
+    }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ResizePlan {
+    float scale_h, scale_w, support_h, support_w;
+    int Kh, Kw;
+    size_t off_tmp, off_xmin_w, off_xsize_w, off_ww, off_xmin_h, off_xsize_h, off_wh, total;
+};
+
+static ResizePlan plan_resize(int h, int w, int oh, int ow, bool cubic) {
+    ResizePlan p;
+    const float interp = cubic ? 4.f : 2.f;
+    p.scale_h = (float)h / (float)oh;  // area_pixel_compute_scale, align_corners=False, no scale_factor
+    p.scale_w = (float)w / (float)ow;
+    p.support_h = p.scale_h >= 1.f ? (interp * 0.5f) * p.scale_h : interp * 0.5f;
+    p.support_w = p.scale_w >= 1.f ? (interp * 0.5f) * p.scale_w : interp * 0.5f;
+    p.Kh = (int)ceilf(p.support_h) * 2 + 1;
+    p.Kw = (int)ceilf(p.support_w) * 2 + 1;
+    size_t o = 0;
+    p.off_tmp = o; o = align_up(o + sizeof(float) * 3 * (size_t)h * ow, 256);
+    p.off_xmin_w = o; o = align_up(o + sizeof(int) * ow, 256);
+    p.off_xsize_w = o; o = align_up(o + sizeof(int) * ow, 256);
+    p.off_ww = o; o = align_up(o + sizeof(float) * (size_t)ow * p.Kw, 256);
+    p.off_xmin_h = o; o = align_up(o + sizeof(int) * oh, 256);
+    p.off_xsize_h = o; o = align_up(o + sizeof(int) * oh, 256);
+    p.off_wh = o; o = align_up(o + sizeof(float) * (size_t)oh * p.Kh, 256);
+    p.total = o;
+    return p;
+}
+
+template <bool CUBIC, bool NORM>
+static int run_resize(const d2s_image *src, int h, int w, void *dst, int dst_dtype, int oh, int ow, const float *mean,
+                      const float *std, void *ws, size_t ws_bytes, d2s_stream_t st) {
+    ResizePlan p = plan_resize(h, w, oh, ow, CUBIC);
+    D2S_REQUIRE(ws && ws_bytes >= p.total, "resize: workspace too small (%zu < %zu)", ws_bytes, p.total);
+    char *b = (char *)ws;
+    AATable tw{(int *)(b + p.off_xmin_w), (int *)(b + p.off_xsize_w), (float *)(b + p.off_ww), p.Kw};
+    AATable th{(int *)(b + p.off_xmin_h), (int *)(b + p.off_xsize_h), (float *)(b + p.off_wh), p.Kh};
+    float *tmp = (float *)(b + p.off_tmp);
+    D2S_LAUNCH((aa_table_kernel<CUBIC>), ceil_div(ow, 128), 128, 0, st, tw, w, ow, p.scale_w, p.support_w);
+    D2S_LAUNCH((aa_table_kernel<CUBIC>), ceil_div(oh, 128), 128, 0, st, th, h, oh, p.scale_h, p.support_h);
+    ImgView v{src->base, src->sc, src->sy, src->sx};
+    dim3 gh(ceil_div(ow, 128), h);
+    switch (src->dtype) {
+        case D2S_U8:  D2S_LAUNCH((aa_resize_h_kernel<uint8_t>), gh, 128, 0, st, v, h, ow, tw, tmp); break;
+        case D2S_F16: D2S_LAUNCH((aa_resize_h_kernel<__half>), gh, 128, 0, st, v, h, ow, tw, tmp); break;
+        case D2S_F32: D2S_LAUNCH((aa_resize_h_kernel<float>), gh, 128, 0, st, v, h, ow, tw, tmp); break;
+        case D2S_BF16: D2S_LAUNCH((aa_resize_h_kernel<__nv_bfloat16>), gh, 128, 0, st, v, h, ow, tw, tmp); break;
+        default: return set_error(D2S_ERR_UNSUPPORTED, "resize: source dtype %d", src->dtype);
+    }
+    dim3 gv(ceil_div(ow, 128), oh, 3);
+    float m0 = mean ? mean[0] : 0, m1 = mean ? mean[1] : 0, m2 = mean ? mean[2] : 0;
+    float s0 = std ? std[0] : 1, s1 = std ? std[1] : 1, s2 = std ? std[2] : 1;
+    switch (dst_dtype) {
+        case D2S_F32: D2S_LAUNCH((aa_resize_v_kernel<float, NORM>), gv, 128, 0, st, tmp, h, ow, oh, th, (float *)dst, m0, m1, m2, s0, s1, s2); break;
+        case D2S_F16: D2S_LAUNCH((aa_resize_v_kernel<__half, NORM>), gv, 128, 0, st, tmp, h, ow, oh, th, (__half *)dst, m0, m1, m2, s0, s1, s2); break;
+        case D2S_BF16: D2S_LAUNCH((aa_resize_v_kernel<__nv_bfloat16, NORM>), gv, 128, 0, st, tmp, h, ow, oh, th, (__nv_bfloat16 *)dst, m0, m1, m2, s0, s1, s2); break;
+        default: return set_error(D2S_ERR_UNSUPPORTED, "resize: destination dtype %d", dst_dtype);
+    }
+    D2S_POST_LAUNCH();
+    return D2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-process
+// ------------------------------------------------------------------------------------------------
+constexpr int kSortCap = 8192;
+
+// Q1: strided subsample -> bitonic sort in shared memory -> k-th smallest / k-th largest  (depth.py:784-794, 849-858)
+template <typename IT, typename CT>
+__global__ void __launch_bounds__(1024) post_bounds_kernel(const IT *__restrict__ d, int n, int step, int ns, int k,
+                                                           float *__restrict__ bounds) {
+    __shared__ float s[kSortCap];
+    for (int i = threadIdx.x; i < kSortCap; i += blockDim.x)
+        s[i] = i < ns ? round_to<CT>(to_f32<IT>(d[(size_t)i * step])) : INFINITY;
+    __syncthreads();
+    for (int size = 2; size <= kSortCap; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < kSortCap / 2; t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                float a = s[lo], b = s[hi];
+                if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        float lo, hi;
+        if (n <= 10) { lo = 0.f; hi = 0.f; }                 // depth.py:845-847
+        else if (k >= ns) { lo = s[0]; hi = s[ns - 1]; }       // tail_count == n -> min/max
+        else { lo = s[k - 1]; hi = s[ns - k]; }
+        bounds[0] = lo; bounds[1] = hi;
+    }
+}
+
+// Q1 (normalise) + Q2 (gamma, foreground scale), per element, each op rounded to CT like ATen's opmath kernels
+template <typename IT, typename CT>
+__global__ void post_point_kernel(const IT *__restrict__ d, int n, const float *__restrict__ bounds, float gamma,
+                                  int fg_on, float fg_exp, float *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lo = bounds[0], hi = bounds[1];
+    float denom = round_to<CT>(fmaxf(round_to<CT>(__fsub_rn(hi, lo)), 1e-6f));
+    float x = round_to<CT>(to_f32<IT>(d[i]));
+    float t = round_to<CT>(__fdiv_rn(round_to<CT>(__fsub_rn(x, lo)), denom));
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    t = round_to<CT>(powf(t, gamma));
+    t = fminf(fmaxf(t, 0.f), 1.f);  // apply_foreground_scale: depth.clamp(0,1)
+    if (fg_on) {
+        float dist = round_to<CT>(__fsub_rn(t, 0.5f));
+        float p = round_to<CT>(powf(fabsf(dist), fg_exp));
+        float sg = dist > 0.f ? 1.f : (dist < 0.f ? -1.f : 0.f);
+        t = round_to<CT>(__fadd_rn(0.5f, round_to<CT>(__fmul_rn(sg, p))));
+        t = fminf(fmaxf(t, 0.f), 1.f);
+    }
+    out[i] = t;
+}
+
+struct BlurW { float w[64]; int k; };
+
+// Q2 anti_alias: separable Gaussian, zero padding (F.conv2d padding=k//2).  AXIS 0: along x, 1: along y.
+// The vertical pass also applies the EMA (Q3) and writes the low-res result.
+template <typename CT, int AXIS>
+__global__ void post_blur_kernel(const float *__restrict__ in, int H, int W, BlurW bw, float *__restrict__ out,
+                                 CT *__restrict__ ema, int ema_valid, float ema_w, CT *__restrict__ out_low) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int r = bw.k / 2;
+    float acc = 0.f;
+    for (int j = 0; j < bw.k; ++j) {
+        int xx = AXIS == 0 ? x + j - r : x, yy = AXIS == 0 ? y : y + j - r;
+        if (xx >= 0 && xx < W && yy >= 0 && yy < H) acc = __fmaf_rn(in[(size_t)yy * W + xx], bw.w[j], acc);
+    }
+    acc = round_to<CT>(acc);
+    size_t o = (size_t)y * W + x;
+    if (AXIS == 1) {
+        if (ema) {  // DepthStabilizer: prev.lerp_(depth, 1-alpha)  (Lerp.h: weight < 0.5 -> self + w*(end-self))
+            if (ema_valid) acc = round_to<CT>(__fmaf_rn(ema_w, __fsub_rn(acc, to_f32<CT>(ema[o])), to_f32<CT>(ema[o])));
+            ema[o] = from_f32<CT>(acc);
+        }
+        if (out_low) out_low[o] = from_f32<CT>(acc);
+    }
+    out[o] = acc;
+}
+
+// pass-through used when the blur is disabled (k < 3): EMA + low-res store only
+template <typename CT>
+__global__ void post_ema_kernel(float *__restrict__ buf, int n, CT *__restrict__ ema, int ema_valid, float ema_w,
+                                CT *__restrict__ out_low) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = buf[i];
+    if (ema) {
+        if (ema_valid) acc = round_to<CT>(__fmaf_rn(ema_w, __fsub_rn(acc, to_f32<CT>(ema[i])), to_f32<CT>(ema[i])));
+        ema[i] = from_f32<CT>(acc);
+    }
+    if (out_low) out_low[i] = from_f32<CT>(acc);
+    buf[i] = acc;
+}
+
+// Q4: upsample_bilinear2d, align_corners=False (UpSampleBilinear2d.cu), fp32 accumulate, rounded to CT then stored as OT
+template <typename CT, typename OT>
+__global__ void post_upsample_kernel(const float *__restrict__ in, int H, int W, OT *__restrict__ out, int oh, int ow,
+                                     float sh, float sw) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= ow) return;
+    float v;
+    if (oh == H && ow == W) v = in[(size_t)y * W + x];
+    else {
+        float h1r = fmaxf(__fmaf_rn(sh, (float)y + 0.5f, -0.5f), 0.f);
+        float w1r = fmaxf(__fmaf_rn(sw, (float)x + 0.5f, -0.5f), 0.f);
+        int h1 = (int)h1r, w1 = (int)w1r;
+        int h1p = (h1 < H - 1) ? 1 : 0, w1p = (w1 < W - 1) ? 1 : 0;
+        float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
+        float w1l = __fsub_rn(w1r, (float)w1), w0l = __fsub_rn(1.f, w1l);
+        const float *r0 = in + (size_t)h1 * W, *r1 = in + (size_t)(h1 + h1p) * W;
+        float top = __fmaf_rn(w0l, r0[w1], __fmul_rn(w1l, r0[w1 + w1p]));
+        float bot = __fmaf_rn(w0l, r1[w1], __fmul_rn(w1l, r1[w1 + w1p]));
+        v = round_to<CT>(__fmaf_rn(h0l, top, __fmul_rn(h1l, bot)));
+    }
+    out[(size_t)y * ow + x] = from_f32<OT>(v);
+}
+
+template <typename CT> static float host_round(float v);
+template <> float host_round<float>(float v) { return v; }
+template <> float host_round<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> float host_round<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// anti_alias's kernel, built the way depth.py:752-757 builds it, each op rounded to CT
+template <typename CT>
+static BlurW make_gauss(float strength) {
+    BlurW bw{};
+    int k = (int)(3 * strength) | 1;
+    bw.k = k;
+    if (k < 3 || k > 63) return bw;
+    double sigma = 0.5 * (double)strength;
+    float denom = (float)(2 * sigma * sigma);
+    float sum = 0.f;
+    for (int j = 0; j < k; ++j) {
+        float c = host_round<CT>((float)(j - k / 2));
+        float sq = host_round<CT>(c * c);
+        float e = host_round<CT>(-sq / denom);
+        bw.w[j] = host_round<CT>(expf(e));
+        sum += bw.w[j];
+    }
+    sum = host_round<CT>(sum);
+    for (int j = 0; j < k; ++j) bw.w[j] = host_round<CT>(bw.w[j] / sum);
+    return bw;
+}
+
+template <typename IT, typename CT>
+static int run_post(const d2s_post_params *p, d2s_stream_t st) {
+    const int H = p->H, W = p->W, n = H * W;
+    size_t need = d2s_postprocess_workspace_bytes(H, W);
+    D2S_REQUIRE(p->workspace && p->workspace_bytes >= need, "d2s_postprocess: workspace too small (%zu < %zu)", p->workspace_bytes, need);
+    float *bounds = (float *)p->workspace;
+    float *bufA = bounds + 64, *bufB = bufA + align_up(n, 64);
+    // depth.py:849-858 integer maths
+    int step = 1, ns = n;
+    if (n > p->subsample_cap) { step = (n + p->subsample_cap - 1) / p->subsample_cap; ns = (n + step - 1) / step; }
+    D2S_REQUIRE(ns <= kSortCap, "d2s_postprocess: subsample of %d values exceeds %d", ns, kSortCap);
+    double lo_q = fmax(0.0, fmin(1.0, (double)p->percentile / 100.0));
+    int k = (int)nearbyint(lo_q * (double)(ns - 1)) + 1;
+    k = k < 1 ? 1 : k; k = k > ns ? ns : k;
+    D2S_LAUNCH((post_bounds_kernel<IT, CT>), 1, 1024, 0, st, (const IT *)p->depth_in, n, step, ns, k, bounds);
+    int fg_on = fabs((double)p->foreground_scale) >= 1e-6;
+    float fg_exp = (float)(1.0 / (1.0 + (double)p->foreground_scale));
+    D2S_LAUNCH((post_point_kernel<IT, CT>), ceil_div(n, 256), 256, 0, st, (const IT *)p->depth_in, n, bounds, p->gamma, fg_on, fg_exp, bufA);
+    BlurW bw = make_gauss<CT>(p->aa_strength);
+    D2S_REQUIRE(bw.k <= 63, "d2s_postprocess: anti-alias kernel size %d too large", bw.k);
+    float ema_w = (float)(1.0 - (double)p->ema_alpha);
+    CT *ema = (CT *)p->ema_state;
+    CT *out_low = (CT *)p->out_lowres;
+    dim3 g(ceil_div(W, 128), H);
+    float *res = bufA;
+    if (bw.k >= 3) {
+        D2S_LAUNCH((post_blur_kernel<CT, 0>), g, 128, 0, st, bufA, H, W, bw, bufB, (CT *)nullptr, 0, 0.f, (CT *)nullptr);
+        D2S_LAUNCH((post_blur_kernel<CT, 1>), g, 128, 0, st, bufB, H, W, bw, bufA, ema, p->ema_valid, ema_w, out_low);
+    } else if (ema || out_low) {
+        D2S_LAUNCH((post_ema_kernel<CT>), ceil_div(n, 256), 256, 0, st, bufA, n, ema, p->ema_valid, ema_w, out_low);
+    }
+    if (p->out) {
+        dim3 gu(ceil_div(p->out_w, 128), p->out_h);
+        float sh = (float)H / (float)p->out_h, sw = (float)W / (float)p->out_w;
+        switch (p->out_dtype) {
+            case D2S_F32: D2S_LAUNCH((post_upsample_kernel<CT, float>), gu, 128, 0, st, res, H, W, (float *)p->out, p->out_h, p->out_w, sh, sw); break;
+            case D2S_F16: D2S_LAUNCH((post_upsample_kernel<CT, __half>), gu, 128, 0, st, res, H, W, (__half *)p->out, p->out_h, p->out_w, sh, sw); break;
+            case D2S_BF16: D2S_LAUNCH((post_upsample_kernel<CT, __nv_bfloat16>), gu, 128, 0, st, res, H, W, (__nv_bfloat16 *)p->out, p->out_h, p->out_w, sh, sw); break;
+            default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: out dtype %d", p->out_dtype);
+        }
+    }
+    D2S_POST_LAUNCH();
+    return D2S_OK;
+}
+
+template <typename IT>
+static int run_post_ct(const d2s_post_params *p, d2s_stream_t st) {
+    switch (p->compute_dtype) {
+        case D2S_F32: return run_post<IT, float>(p, st);
+        case D2S_F16: return run_post<IT, __half>(p, st);
+        case D2S_BF16: return run_post<IT, __nv_bfloat16>(p, st);
+        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: compute dtype %d", p->compute_dtype);
+    }
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_model_input_shape(int h, int w, int target, int patch, int *new_h, int *new_w) {
+    D2S_REQUIRE(h > 0 && w > 0 && target > 0 && patch > 0 && new_h && new_w, "d2s_model_input_shape: bad arguments");
+    // depth.py:676-692 (python floats are doubles; round() is half-to-even)
+    int longest = h > w ? h : w;
+    double scale = longest != target ? (double)target / (double)longest : 1.0;
+    long sh = (long)nearbyint((double)h * scale), sw = (long)nearbyint((double)w * scale);
+    sh = sh < 1 ? 1 : sh; sw = sw < 1 ? 1 : sw;
+    auto nearest = [patch](long x) { long down = (x / patch) * patch, up = down + patch; return (up - x) <= (x - down) ? up : down; };
+    long nh = nearest(sh), nw = nearest(sw);
+    *new_h = (int)(nh < 1 ? 1 : nh); *new_w = (int)(nw < 1 ? 1 : nw);
+    return D2S_OK;
+}
+
+extern "C" size_t d2s_preprocess_workspace_bytes(int h, int w, int new_h, int new_w) {
+    if (h <= 0 || w <= 0 || new_h <= 0 || new_w <= 0) return 0;
+    size_t a = plan_resize(h, w, new_h, new_w, true).total, b = plan_resize(h, w, new_h, new_w, false).total;
+    return a > b ? a : b;
+}
+
+extern "C" int d2s_preprocess(const d2s_image *src, int h, int w, void *dst, int dst_dtype, int new_h, int new_w,
+                              const float mean[3], const float std[3], void *workspace, size_t workspace_bytes,
+                              d2s_stream_t stream) {
+    D2S_REQUIRE(src && src->base && dst && h > 0 && w > 0 && new_h > 0 && new_w > 0, "d2s_preprocess: bad arguments");
+    D2S_REQUIRE(mean && std, "d2s_preprocess: mean/std required");
+    return run_resize<true, true>(src, h, w, dst, dst_dtype, new_h, new_w, mean, std, workspace, workspace_bytes, stream);
+}
+
+extern "C" int d2s_process(const uint8_t *frame, int h0, int w0, int channels, void *out, int out_dtype, int h, int w,
+                           d2s_stream_t stream) {
+    D2S_REQUIRE(frame && out && h0 > 0 && w0 > 0 && (channels == 3 || channels == 4), "d2s_process: bad arguments");
+    D2S_REQUIRE(h > 0 && w > 0, "d2s_process: bad output size");
+    if (h == h0 && w == w0) {
+        int grid = ceil_div(ceil_div((long long)h * w, 4), 256);
+        switch (out_dtype) {
+            case D2S_F16: D2S_LAUNCH((swizzle_chw_kernel<__half>), grid, 256, 0, stream, frame, h, w, channels, (__half *)out); break;
+            case D2S_F32: D2S_LAUNCH((swizzle_chw_kernel<float>), grid, 256, 0, stream, frame, h, w, channels, (float *)out); break;
+            case D2S_U8:  D2S_LAUNCH((swizzle_chw_kernel<uint8_t>), grid, 256, 0, stream, frame, h, w, channels, (uint8_t *)out); break;
+            case D2S_BF16: D2S_LAUNCH((swizzle_chw_kernel<__nv_bfloat16>), grid, 256, 0, stream, frame, h, w, channels, (__nv_bfloat16 *)out); break;
+            default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_process: out dtype %d", out_dtype);
+        }
+        D2S_POST_LAUNCH();
+        return D2S_OK;
+    }
+    // bilinear + antialias downscale (depth.py:560-566).  Scratch is stream-ordered and library-owned.
+    d2s_image src{};
+    src.base = (void *)(frame + 2); src.dtype = D2S_U8; src.sc = -1; src.sy = (int64_t)w0 * channels; src.sx = channels;
+    size_t bytes = plan_resize(h0, w0, h, w, false).total;
+    void *ws = nullptr;
+    D2S_CHECK_CUDA(cudaMallocAsync(&ws, bytes, (cudaStream_t)stream));
+    int rc = run_resize<false, false>(&src, h0, w0, out, out_dtype, h, w, nullptr, nullptr, ws, bytes, stream);
+    cudaFreeAsync(ws, (cudaStream_t)stream);
+    return rc;
+}
+
+extern "C" size_t d2s_postprocess_workspace_bytes(int H, int W) {
+    if (H <= 0 || W <= 0) return 0;
+    return sizeof(float) * (64 + 2 * align_up((size_t)H * W, 64));
+}
+
+extern "C" int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream) {
+    D2S_REQUIRE(p && p->depth_in && p->H > 0 && p->W > 0, "d2s_postprocess: bad arguments");
+    D2S_REQUIRE(p->out == nullptr || (p->out_h > 0 && p->out_w > 0), "d2s_postprocess: bad output size");
+    D2S_REQUIRE(p->subsample_cap >= 1, "d2s_postprocess: subsample_cap");
+    if (p->metric) return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: metric-depth inversion (depth.py:837-841) not implemented");
+    switch (p->in_dtype) {
+        case D2S_F32: return run_post_ct<float>(p, stream);
+        case D2S_F16: return run_post_ct<__half>(p, stream);
+        case D2S_BF16: return run_post_ct<__nv_bfloat16>(p, stream);
+        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: in dtype %d", p->in_dtype);
+    }
+}

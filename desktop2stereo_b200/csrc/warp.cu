@@ -149,35 +149,35 @@ __device__ __forceinline__ void cat_pixel(const WarpK &k, const RowCtx *rows, in
     eye_pixel<RT, DT>(k, row, e, ey, ex, rgb);
 }
 
+// 4 consecutive elements of OT packed into one register vector (16 B f32, 8 B f16/bf16, 4 B u8)
+template <typename OT> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; static __device__ __forceinline__ type pack(float a, float b, float c, float d) { return make_float4(a, b, c, d); } };
+template <> struct Vec4<__half> { typedef uint2 type; static __device__ __forceinline__ type pack(float a, float b, float c, float d) {
+    __half2 lo = __halves2half2(__float2half_rn(a), __float2half_rn(b)), hi = __halves2half2(__float2half_rn(c), __float2half_rn(d));
+    return make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi); } };
+template <> struct Vec4<__nv_bfloat16> { typedef uint2 type; static __device__ __forceinline__ type pack(float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __halves2bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b)), hi = __halves2bfloat162(__float2bfloat16_rn(c), __float2bfloat16_rn(d));
+    return make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi); } };
+template <> struct Vec4<uint8_t> { typedef uint32_t type; static __device__ __forceinline__ type pack(float a, float b, float c, float d) {
+    return (uint32_t)from_f32<uint8_t>(a) | ((uint32_t)from_f32<uint8_t>(b) << 8) | ((uint32_t)from_f32<uint8_t>(c) << 16) | ((uint32_t)from_f32<uint8_t>(d) << 24); } };
+
 // 4 pixels x 3 channels -> memory (vectorised when the layout allows)
 template <typename OT>
 __device__ __forceinline__ void store_px4(const WarpK &k, int oy, int ox, int n, const float (*v)[3]) {
+    typedef typename Vec4<OT>::type V;
     OT *base = (OT *)k.out + (long long)oy * k.osy + (long long)ox * k.osx;
-    constexpr int kVecBytes = 4 * sizeof(OT);  // 4 elements: 16 B (f32), 8 B (f16), 4 B (u8)
-    if (n == 4 && k.osx == 3 && k.osc == 1 && ((uintptr_t)base % kVecBytes) == 0) {
+    if (n == 4 && k.osx == 3 && k.osc == 1 && ((uintptr_t)base % sizeof(V)) == 0) {
         // HWC: 12 contiguous elements
-        OT tmp[12];
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) tmp[p * 3 + c] = from_f32<OT>(v[p][c]);
-        if (sizeof(OT) == 4) { float4 *d = (float4 *)base; const float4 *s = (const float4 *)tmp; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
-        else if (sizeof(OT) == 2) { uint2 *d = (uint2 *)base; const uint2 *s = (const uint2 *)tmp; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
-        else { uint32_t *d = (uint32_t *)base; const uint32_t *s = (const uint32_t *)tmp; d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+        V *d = (V *)base;
+        d[0] = Vec4<OT>::pack(v[0][0], v[0][1], v[0][2], v[1][0]);
+        d[1] = Vec4<OT>::pack(v[1][1], v[1][2], v[2][0], v[2][1]);
+        d[2] = Vec4<OT>::pack(v[2][2], v[3][0], v[3][1], v[3][2]);
         return;
     }
-    if (n == 4 && k.osx == 1 && ((uintptr_t)base % kVecBytes) == 0 && ((k.osc * (long long)sizeof(OT)) % kVecBytes) == 0) {
+    if (n == 4 && k.osx == 1 && ((uintptr_t)base % sizeof(V)) == 0 && ((k.osc * (long long)sizeof(OT)) % sizeof(V)) == 0) {
         // CHW: 4 contiguous elements per plane
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            OT tmp[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) tmp[p] = from_f32<OT>(v[p][c]);
-            OT *d = base + c * k.osc;
-            if (sizeof(OT) == 4) *(float4 *)d = *(const float4 *)tmp;
-            else if (sizeof(OT) == 2) *(uint2 *)d = *(const uint2 *)tmp;
-            else *(uint32_t *)d = *(const uint32_t *)tmp;
-        }
+        for (int c = 0; c < 3; ++c) *(V *)(base + c * k.osc) = Vec4<OT>::pack(v[0][c], v[1][c], v[2][c], v[3][c]);
         return;
     }
     for (int p = 0; p < n; ++p)
@@ -243,6 +243,7 @@ static int launch_out(const WarpK &k, int out_dtype, dim3 grid, dim3 block, d2s_
         case D2S_F32: D2S_LAUNCH((warp_sbs_kernel<RT, DT, float>), grid, block, 0, st, k); break;
         case D2S_F16: D2S_LAUNCH((warp_sbs_kernel<RT, DT, __half>), grid, block, 0, st, k); break;
         case D2S_U8:  D2S_LAUNCH((warp_sbs_kernel<RT, DT, uint8_t>), grid, block, 0, st, k); break;
+        case D2S_BF16: D2S_LAUNCH((warp_sbs_kernel<RT, DT, __nv_bfloat16>), grid, block, 0, st, k); break;
         default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs: out dtype %d unsupported", out_dtype);
     }
     return D2S_OK;
@@ -295,8 +296,8 @@ extern "C" int d2s_make_sbs(const d2s_warp_params *p, d2s_stream_t stream) {
     k.ow = k.half ? k.pw : (k.tab ? k.pw : 2 * k.pw);
     k.gather = p->warp_mode == D2S_WARP_GATHER;
     k.rgb_round = p->rgb_round_to_depth_dtype != 0;
-    k.conv = p->convergence; k.ratio = p->depth_ratio;
-    k.max_px = (float)((double)p->ipd_uv * (double)p->w);  // python: ipd_uv * W (double), then fp32 scalar
+    k.conv = (float)p->convergence; k.ratio = (float)p->depth_ratio;
+    k.max_px = (float)(p->ipd_uv * (double)p->w);  // python: ipd_uv * W (double), then fp32 scalar
     k.strength = (float)0.05;
     k.two_over_wm1 = (float)(2.0 / (double)(p->w - 1));
     k.xstep = 2.0f / (float)(p->w - 1); k.xhalf = p->w / 2;

@@ -68,7 +68,7 @@ typedef struct d2s_warp_params {
     int32_t depth_h, depth_w; /* == h,w: full-res depth.  Otherwise the bilinear align_corners=False
                                  upsample of depth.py:1998-2004 is evaluated inside the gather. */
     int32_t h, w;
-    float ipd_uv, depth_ratio, convergence;
+    double ipd_uv, depth_ratio, convergence; /* python floats: scalars are rounded to fp32 only after ipd_uv*W (depth.py:2146) */
     int32_t display_mode; /* enum d2s_display_mode */
     int32_t fill_16_9;
     int32_t warp_mode;    /* enum d2s_warp_mode */
@@ -148,6 +148,7 @@ typedef struct d2s_post_params {
     void *ema_state;      /* optional [H,W] compute_dtype persistent buffer (DepthStabilizer.prev) */
     int32_t ema_valid;    /* 0: first frame (state := depth), 1: lerp */
     float ema_alpha;      /* 0.9 */
+    void *out_lowres;     /* optional [H,W] compute_dtype: the post-processed (+EMA) map before the upsample */
     void *workspace; size_t workspace_bytes;
 } d2s_post_params;
 size_t d2s_postprocess_workspace_bytes(int H, int W);

@@ -73,6 +73,128 @@ def gen_warp(depth_mod):
     print(f"warp.npz: {i} cases")
 
 
+def _cuda_branch_process(depth_mod):
+    """The reference defines its CUDA `process` only when IS_CUDA is true at import (depth.py:540-566).
+    Compile that exact FunctionDef from the reference source and run it on CPU in the module's namespace."""
+    import ast
+    src = open(depth_mod.__file__).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.If) and isinstance(node.test, ast.Name) and node.test.id == "IS_CUDA":
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == "process":
+                    ns = dict(depth_mod.__dict__)
+                    exec(compile(ast.Module(body=[fn], type_ignores=[]), depth_mod.__file__, "exec"), ns)
+                    return ns["process"]
+    raise RuntimeError("CUDA-branch process() not found in the reference")
+
+
+def synth_depth(seed, H, W):
+    """Raw-depth-like positive map, regenerable on any box from the seed (tests rebuild it)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    d = 2.0 + np.sin(xx / W * 7.0 + rng.random() * 6) + np.cos(yy / H * 4.0 + rng.random() * 6)
+    d += 0.8 * (np.hypot(xx - W * rng.random(), yy - H * rng.random()) < min(H, W) / 4)
+    d += 0.05 * rng.standard_normal((H, W)).astype(np.float32)
+    return np.maximum(d, 0).astype(np.float32)
+
+
+def synth_frame(seed, h, w, ch=4):
+    """BGRA/BGR u8 frame: smooth gradients + blocks + noise (regenerable from the seed)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([128 + 100 * np.sin(xx / w * (3 + c) + c) * np.cos(yy / h * (2 + c)) for c in range(3)], -1)
+    img[h // 4: h // 2, w // 3: 2 * w // 3] += 60
+    img += rng.normal(0, 12, img.shape)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    if ch == 4:
+        img = np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], -1)
+    return img
+
+
+def gen_pre(depth_mod):
+    """process() [CUDA branch], _resize_patch_aligned_t [CUDA branch] and the /255, mean/std normalisation."""
+    out = {"versions": _versions()}
+    proc = _cuda_branch_process(depth_mod)
+    depth_mod.IS_CUDA = True
+    try:
+        cases = [(0, 135, 240, 4, 135), (1, 270, 480, 4, 135), (2, 200, 301, 3, 120)]
+        for (seed, h, w, ch, target_h) in cases:
+            frame = synth_frame(seed, h, w, ch)
+            for dt in (torch.float32, torch.float16):
+                if dt == torch.float16 and target_h < h:
+                    continue  # ATen's CPU antialias kernel has no Half implementation
+                old = depth_mod.DTYPE
+                depth_mod.DTYPE = dt
+                ns_proc = proc.__globals__
+                ns_proc["DTYPE"] = dt
+                rgb = proc(frame.copy(), target_h)
+                depth_mod.DTYPE = old
+                arr = rgb.float().numpy()
+                out[f"proc{seed}_{str(dt).split('.')[1]}"] = arr.astype(np.uint8) if target_h >= h else arr
+            out[f"proc{seed}_meta"] = np.array([seed, h, w, ch, target_h])
+        # resize + normalise: u8 CHW input (fp32 arithmetic) at several aspect ratios, incl. 16:9 -> 294x518-like
+        for (seed, h, w, target) in [(10, 135, 240, 70), (11, 240, 135, 70), (12, 224, 224, 98), (13, 270, 480, 126), (14, 98, 98, 98)]:
+            frame = synth_frame(seed, h, w, 3)
+            t = torch.from_numpy(frame[..., ::-1].copy()).permute(2, 0, 1).unsqueeze(0)  # RGB CHW u8
+            r = depth_mod._resize_patch_aligned_t(t, target, 14)
+            x = r.to(torch.float32) / 255.0
+            x = (x - depth_mod.MEAN) / depth_mod.STD
+            out[f"pre{seed}_resized"] = r.float().numpy()[0] if r.dtype != torch.uint8 else r.numpy()[0].astype(np.float32)
+            out[f"pre{seed}_input"] = x.numpy()[0]
+            out[f"pre{seed}_meta"] = np.array([seed, h, w, target])
+        # shapes table (integer maths, bit-exact target)
+        shapes = []
+        for (h, w) in [(1080, 1920), (2160, 3840), (518, 518), (720, 1280), (1440, 2560), (1200, 1600), (1080, 2560), (333, 777), (14, 14), (100, 37)]:
+            for target in (518, 336, 294, 70):
+                t = torch.zeros(1, 3, h, w, dtype=torch.uint8)
+                r = depth_mod._resize_patch_aligned_t(t, target, 14) if max(h, w) * 3 < 20000 else None
+                shapes.append([h, w, target, r.shape[2], r.shape[3]])
+        out["shapes"] = np.array(shapes)
+    finally:
+        depth_mod.IS_CUDA = False
+    np.savez_compressed(os.path.join(GOLDEN, "pre.npz"), **out)
+    print("pre.npz written")
+
+
+def gen_post(depth_mod):
+    """post_process_depth, DepthStabilizer (3-frame EMA) and the final upsample, in fp32 / bf16 / fp16."""
+    out = {"versions": _versions()}
+    i = 0
+    for (H, W, oh, ow) in [(42, 70, 135, 240), (70, 70, 98, 98), (294, 518, 540, 960)]:
+        for dt in (torch.float32, torch.bfloat16, torch.float16):
+            big = H > 100
+            if big and dt != torch.float32:
+                continue
+            depth_mod.depth_stabilizer.prev = None
+            frames = []
+            for f in range(3):
+                raw = torch.from_numpy(synth_depth(100 + i * 10 + f, H, W)).to(dt)
+                try:
+                    pp = depth_mod.post_process_depth(raw.clone())
+                except RuntimeError as e:  # an op missing for this dtype on CPU
+                    print("skip", dt, e)
+                    pp = None
+                    break
+                st = depth_mod.depth_stabilizer(pp.clone())
+                up = torch.nn.functional.interpolate(st[None, None], size=(oh, ow), mode="bilinear", align_corners=False)[0, 0]
+                frames.append((pp.float().numpy(), st.float().numpy().copy(), up.float().numpy()))
+            if pp is None:
+                continue
+            sub = 7 if big else 1
+            for f, (pp, st, up) in enumerate(frames):
+                out[f"post{i}_f{f}_pp"] = pp[::sub, ::sub]
+                out[f"post{i}_f{f}_ema"] = st[::sub, ::sub]
+                out[f"post{i}_f{f}_up"] = up[::sub * 3, ::sub * 3]
+            out[f"post{i}_meta"] = np.array([H, W, oh, ow, {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dt], sub, 100 + i * 10])
+            i += 1
+    out["n_cases"] = np.array(i)
+    out["fg_aa"] = np.array([depth_mod.FOREGROUND_SCALE, depth_mod.AA_STRENGTH], np.float64)
+    depth_mod.depth_stabilizer.prev = None
+    np.savez_compressed(os.path.join(GOLDEN, "post.npz"), **out)
+    print(f"post.npz: {i} cases")
+
+
 def main(argv):
     os.makedirs(GOLDEN, exist_ok=True)
     what = set(argv) or {"warp", "post", "pre", "model", "e2e"}
