@@ -70,6 +70,10 @@ SYMBOLS = {
     "d2s_postprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "d2s_postprocess": (C.c_int, [C.POINTER(PostParams), C.c_void_p]),
     "d2s_overlay_fps": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_char_p, C.c_void_p]),
+    "d2s_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "d2s_debug_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "d2s_debug_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "d2s_last_error": (C.c_char_p, []),
     "d2s_version": (C.c_char_p, []),
 }

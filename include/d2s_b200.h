@@ -157,6 +157,16 @@ int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream);
 /* overlay_fps: blends the "FPS: xx.x" glyph mask into an RGB image in place. */
 int d2s_overlay_fps(const d2s_image *rgb, int h, int w, const char *text, d2s_stream_t stream);
 
+/* ---- kernel-level parity hooks (used by tests/ only; fp16 operands, row-major) ----
+ * d2s_debug_gemm:      C[M,N] = act(A[M,K] * Bw[N,K]^T + bias)   and/or   x32[M,N] += A*Bw^T + bias   (tcgen05 GEMM)
+ * d2s_debug_conv3x3:   NHWC [B,H,W,Cp] (*) Wt[N, 9*Cp] (k = (ky*3+kx)*Cp + c), pad 1, + bias, act, + res1; optional relu copy
+ * d2s_debug_attention: qkv [B,N,3D] -> softmax(q k^T / 8) v, [B,N,D], head dim 64 */
+int d2s_debug_gemm(const void *A, const void *Bw, const float *bias, void *C, int M, int N, int K, int act,
+                   float *x32_accumulate, d2s_stream_t stream);
+int d2s_debug_conv3x3(const void *A, const void *Wt, const float *bias, void *C, int B, int H, int W, int Cp, int N, int act,
+                      const void *res1, void *c_relu, d2s_stream_t stream);
+int d2s_debug_attention(const void *qkv, void *out, int B, int N, int D, int heads, d2s_stream_t stream);
+
 const char *d2s_last_error(void);
 const char *d2s_version(void);
 

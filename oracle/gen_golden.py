@@ -195,6 +195,37 @@ def gen_post(depth_mod):
     print(f"post.npz: {i} cases")
 
 
+TINY = dict(hidden=128, layers=4, heads=2, out_indices=[1, 2, 3, 4], neck=[24, 48, 96, 192], fusion=64)
+MODEL_CASES = [  # (name, variant, tiny cfg, seed, B, H, W, stored stride)
+    ("tiny_70x98", "Small", TINY, 3, 2, 70, 98, 1),
+    ("tiny_518", "Small", TINY, 4, 1, 518, 518, 7),
+    ("small_70x126", "Small", None, 5, 1, 70, 126, 1),
+]
+
+
+def model_input(seed, B, H, W):
+    """Normalised-image-like input, regenerable from the seed."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    base = np.stack([np.sin(xx / W * (4 + c) + b) * np.cos(yy / H * (3 + c) - b) for b in range(B) for c in range(3)], 0)
+    x = base.reshape(B, 3, H, W) * 1.5 + rng.normal(0, 0.3, (B, 3, H, W))
+    return x.astype(np.float32)
+
+
+def gen_model(depth_mod):
+    """predicted_depth of HF's DepthAnythingForDepthEstimation (fp32, no autocast) on seeded weights and inputs."""
+    from .ref_harness import make_hf_model
+    out = {"versions": _versions()}
+    for (name, variant, tiny, seed, B, H, W, stride) in MODEL_CASES:
+        model = make_hf_model(variant, seed, tiny)
+        x = torch.from_numpy(model_input(seed, B, H, W))
+        with torch.no_grad():
+            d = model(pixel_values=x).predicted_depth
+        out[name] = d.numpy()[:, ::stride, ::stride]
+        print(name, tuple(d.shape), float(d.min()), float(d.max()))
+    np.savez_compressed(os.path.join(GOLDEN, "model.npz"), **out)
+
+
 def main(argv):
     os.makedirs(GOLDEN, exist_ok=True)
     what = set(argv) or {"warp", "post", "pre", "model", "e2e"}

@@ -65,6 +65,15 @@ def randomize_constant_params(model, seed: int):
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, p in sorted(model.named_parameters()):
+            if name.endswith("weight") and p.dim() >= 2:
+                # variance-preserving re-draw: HF's default trunc-normal(0.02) init makes every activation collapse
+                # towards 0 and the final ReLU output identically 0, which would make parity tests vacuous
+                fan_in = p[0].numel() if "resize" not in name or p.dim() != 4 or "layers.3" in name else p.shape[0] * p[0, 0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) * (1.0 / fan_in ** 0.5))
+                continue
+            if name == "head.conv3.bias":
+                p.fill_(0.5)
+                continue
             if name.endswith("lambda1"):
                 p.copy_(0.5 + torch.rand(p.shape, generator=g))
             elif "norm" in name and name.endswith("weight"):
