@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — end-to-end frames/s of the depth-inference + SBS-warp hot path (BASELINE.json metric).
+
+Workload at every N: BASELINE.json configs[1] per GPU — Depth Anything V2-Base, 1080p BGRA frames, batch 1,
+Full-SBS (model input 294x518, 778 tokens) — synthetic frames, seeded random-init weights (no network).  Frames shard
+across ranks with no per-frame collective ("scaling": "weak"); the only collective is one NCCL broadcast of the packed
+weight blob at init.
+
+    python bench.py --gpus 1 --steps 200 --warmup 10          # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1      # the reference's CPU path (oracle port), host cores
+One JSON line on stdout (rank 0).  `value` = frames/s with frames resident in HBM; `e2e` = the same through the
+reference-facing calls process -> predict_depth -> make_sbs with HOST buffers (H2D of the frame and D2H of the float32
+SBS frame inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 1080, 1920
+VARIANT = "Base"
+DISPLAY_MODE = "Full-SBS"
+DEPTH_RATIO = 2.0
+SEED = 0
+
+
+def model_flops(cfg, Hm, Wm):
+    """Algorithmic FLOPs (2*MAC) of one frame through the network (SURVEY §8d formulas)."""
+    D, L, F = cfg.hidden, cfg.layers, cfg.fusion
+    c = [cfg.neck[i] for i in range(4)]
+    ph, pw = Hm // 14, Wm // 14
+    P, N = ph * pw, ph * pw + 1
+    fl = 2 * P * 588 * D + L * (24 * N * D * D + 4 * N * N * D)
+    hs = [4 * ph, 2 * ph, ph, (ph - 1) // 2 + 1]
+    ws = [4 * pw, 2 * pw, pw, (pw - 1) // 2 + 1]
+    fl += sum(2 * P * D * ci for ci in c) + 2 * P * c[0] * 16 * c[0] + 2 * P * c[1] * 4 * c[1] + 2 * hs[3] * ws[3] * 9 * c[3] * c[3]
+    fl += sum(2 * hs[i] * ws[i] * 9 * c[i] * F for i in range(4))
+    for j in range(4):
+        lv = 3 - j
+        n_rcu = 1 if j == 0 else 2
+        fl += n_rcu * 2 * (2 * hs[lv] * ws[lv] * 9 * F * F)
+        oh, ow = (hs[lv - 1], ws[lv - 1]) if j < 3 else (2 * hs[lv], 2 * ws[lv])
+        fl += 2 * oh * ow * F * F
+    fl += 2 * (8 * ph) * (8 * pw) * 9 * F * (F // 2) + 2 * Hm * Wm * 9 * (F // 2) * 32 + 2 * Hm * Wm * 32
+    return fl
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_hf_model(variant=VARIANT, seed=SEED):
+    from oracle.ref_harness import make_hf_model   # seeded random-init weights (no checkpoints offline)
+    return make_hf_model(variant, seed)
+
+
+def cpu_reference_fps(n_frames, warmup, threads):
+    """The reference's CPU path (oracle port: HF model under bf16 autocast + torch pre/post/warp) on the host cores."""
+    import numpy as np
+    import torch
+    from oracle.cpu_pipeline import ReferenceCPUPipeline
+    torch.set_num_threads(threads)
+    pipe = ReferenceCPUPipeline(build_hf_model(), 518)
+    rng = np.random.default_rng(SEED)
+    frames = [rng.integers(0, 256, (H, W, 4), dtype=np.uint8) for _ in range(2)]
+    for i in range(warmup):
+        pipe.frame(frames[i % 2], DISPLAY_MODE, DEPTH_RATIO)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        out = pipe.frame(frames[i % 2], DISPLAY_MODE, DEPTH_RATIO)
+    dt = time.perf_counter() - t0
+    assert out.shape == (H, 2 * W, 3)
+    return n_frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    fps, dt = cpu_reference_fps(args.steps, max(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 autocast (CPU)", "data": "synthetic",
+        "config": {"workload": f"DA-V2-{VARIANT}, 1080p BGRA batch=1 -> {DISPLAY_MODE} (model input 294x518)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} frames of the same 1080p workload, 1 frame per step"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from desktop2stereo_b200 import _lib, depth
+    from desktop2stereo_b200.engine import B200Engine
+    from desktop2stereo_b200.stereo import make_sbs_core
+    from desktop2stereo_b200.weights import config_from_hf, pack_state_dict
+    L = _lib.lib()
+    warmup = max(args.warmup, 3)
+
+    # ---- weights: rank 0 packs, one NCCL broadcast over NVLink, every rank builds its own engine ----
+    from transformers import DepthAnythingConfig  # config only on ranks > 0
+    if rank == 0:
+        model = build_hf_model()
+        cfg = config_from_hf(model.config)
+        blob = torch.from_numpy(pack_state_dict(model.state_dict(), cfg))
+        hf_cfg_json = model.config.to_json_string()
+        del model
+    if world > 1:
+        meta = [hf_cfg_json, blob.numel()] if rank == 0 else [None, None]
+        dist.broadcast_object_list(meta, src=0)
+        if rank != 0:
+            cfg = config_from_hf(DepthAnythingConfig.from_dict(json.loads(meta[0])))
+        dblob = blob.to(dev) if rank == 0 else torch.empty(meta[1], dtype=torch.float32, device=dev)
+        dist.broadcast(dblob, src=0)
+        blob = dblob.cpu()
+        del dblob
+    engine = B200Engine(blob.numpy(), cfg, dev, out_dtype=torch.float16)
+    depth.init(engine=engine, device=dev)
+
+    # ---- synthetic frames: a ring larger than L2 so no timed iteration re-reads a cached frame ----
+    RING = 24
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    frames = [torch.randint(0, 256, (H, W, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(RING)]
+    host_frames = [f.cpu().pin_memory() for f in frames[:4]]   # pinned host copies for the end-to-end leg
+    host_np = [t.numpy() for t in host_frames]
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stage_ev = []
+
+    def step_device(i, record=False):
+        f = frames[i % RING]
+        if record:
+            e = [ev() for _ in range(4)]
+            e[0].record()
+        rgb = depth.process(f, H)
+        if record:
+            e[1].record()
+        d = depth.predict_depth(rgb)
+        if record:
+            e[2].record()
+        sbs = make_sbs_core(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC")
+        if record:
+            e[3].record()
+            stage_ev.append(e)
+        return sbs
+
+    def step_e2e(i):
+        rgb = depth.process(host_np[i % 4], H)            # H2D of the pinned BGRA frame happens here (depth.py:547)
+        d = depth.predict_depth(rgb)
+        return depth.make_sbs(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE)   # D2H float32 HWC + stream sync
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps, **kw):
+        barrier(); torch.cuda.synchronize()
+        s, e = ev(), ev()
+        s.record()
+        for i in range(steps):
+            fn(i, **kw)
+        e.record()
+        torch.cuda.synchronize(); barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(warmup):
+        out = step_device(i)
+    assert tuple(out.shape) == (H, 2 * W, 3)
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = L.d2s_launch_count()
+    ms = timed(step_device, args.steps, record=True)
+    launches = L.d2s_launch_count() - launches0
+    clk = clocks.stop()
+    fps = world * args.steps / (ms / 1e3)
+
+    # per-stage device times from the events recorded inside the timed region
+    torch.cuda.synchronize()
+    st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in stage_ev])
+    stage_ms = dict(zip(["process", "predict_depth", "warp"], st.mean(0).tolist()))
+
+    for i in range(warmup):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    fps_e2e = world * args.steps / (ms_e2e / 1e3)
+    h2d, d2h = H * W * 4, H * 2 * W * 3 * 4
+
+    # ---- rooflines (denominators: MEASURED_PEAKS.json, else the profiling guide's fallback) ----
+    peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); src = "measured"
+    except Exception:
+        pass
+    # warp kernel: fp16 CHW rgb in (6 B/px) + fp16 depth in (2 B/px) + fp32 HWC Full-SBS out (24 B/px)
+    warp_bytes = H * W * (6 + 2 + 24)
+    warp_gbs = warp_bytes / (stage_ms["warp"] * 1e-3) / 1e9
+    # the network is replayed as ONE CUDA-graph launch per frame; its kernels are timed together via predict_depth
+    Hm, Wm = 294, 518
+    gflop = model_flops(cfg, Hm, Wm) / 1e9
+    net_tflops = gflop / (stage_ms["predict_depth"] * 1e-3) / 1e3
+    dominant = max(stage_ms, key=stage_ms.get)
+    roofline_warp = {"kernel": "warp_sbs_kernel", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": src,
+                     "bytes_per_launch": warp_bytes, "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS"}
+    roofline_net = {"kernel": "depth network (one graph launch: preprocess + ViT-B + DPT + postprocess)", "bound": "tensor",
+                    "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": src,
+                    "gflop_per_launch": gflop}
+    roofline = roofline_warp if dominant == "warp" else roofline_net
+
+    line = {
+        "metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": fps, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
+        "config": {"workload": f"DA-V2-{VARIANT}, 1080p BGRA batch=1 -> {DISPLAY_MODE} (model input 294x518, 778 tokens), per GPU",
+                   "l2": f"ring of {RING} distinct frames ({RING * H * W * 4 / 1e6:.0f} MB) > 126 MB L2", "parallelism": f"frames sharded x{world}",
+                   "weights": "seeded random init, one NCCL broadcast at init" if world > 1 else "seeded random init"},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps, "api": "process -> predict_depth -> make_sbs (float32 HWC ndarray out)"},
+        "gpu_launches": int(launches), "clocks": clk, "stage_ms": stage_ms,
+        "roofline": roofline, "roofline_warp": roofline_warp, "roofline_net": roofline_net,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cfps, cdt = cpu_reference_fps(args.cpu_frames, 1, threads)
+        line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_frames} frames of the same 1080p workload after 1 warm-up ({cdt:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

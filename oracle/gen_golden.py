@@ -226,6 +226,30 @@ def gen_model(depth_mod):
     np.savez_compressed(os.path.join(GOLDEN, "model.npz"), **out)
 
 
+E2E = dict(seed=11, h=90, w=160, depth_resolution=70)
+
+
+def gen_e2e(_unused):
+    """process -> predict_depth -> make_sbs of the reference on one seeded frame, tiny seeded model, fp32 (autocast
+    disabled so the golden is a precision reference), CUDA-branch resize semantics, EMA off."""
+    import contextlib
+    dm = load_reference("Small", depth_resolution=E2E["depth_resolution"], fp16=False, seed=E2E["seed"], tiny=TINY)
+    dm.maybe_autocast = lambda *a, **k: contextlib.nullcontext()
+    proc = _cuda_branch_process(dm)
+    dm.IS_CUDA = True
+    try:
+        frame = synth_frame(E2E["seed"], E2E["h"], E2E["w"], 4)
+        rgb = proc(frame.copy(), E2E["h"])
+        depth = dm.predict_depth(rgb, use_temporal_smooth=False)
+        out = {"versions": _versions(), "depth": depth.float().numpy()}
+        for mode in ("Half-SBS", "Full-SBS"):
+            out["sbs_" + mode] = dm.make_sbs(rgb, depth, ipd_uv=0.064, depth_ratio=4.0, convergence=0.0, display_mode=mode).astype(np.float16)
+        print("e2e depth", tuple(depth.shape), depth.dtype, float(depth.min()), float(depth.max()), float(depth.mean()))
+    finally:
+        dm.IS_CUDA = False
+    np.savez_compressed(os.path.join(GOLDEN, "e2e.npz"), **out)
+
+
 def main(argv):
     os.makedirs(GOLDEN, exist_ok=True)
     what = set(argv) or {"warp", "post", "pre", "model", "e2e"}
