@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--slots", type=int, default=3, help="frames in flight (CUDA streams) in the pipelined legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,41 +201,20 @@ def main():
     host_frames = [f.cpu().pin_memory() for f in frames[:4]]   # pinned host copies for the end-to-end leg
     host_np = [t.numpy() for t in host_frames]
 
+    from desktop2stereo_b200.pipeline import StereoPipeline
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ev = []
-
-    def step_device(i, record=False):
-        f = frames[i % RING]
-        if record:
-            e = [ev() for _ in range(4)]
-            e[0].record()
-        rgb = depth.process(f, H)
-        if record:
-            e[1].record()
-        d = depth.predict_depth(rgb)
-        if record:
-            e[2].record()
-        sbs = make_sbs_core(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC")
-        if record:
-            e[3].record()
-            stage_ev.append(e)
-        return sbs
-
-    def step_e2e(i):
-        rgb = depth.process(host_np[i % 4], H)            # H2D of the pinned BGRA frame happens here (depth.py:547)
-        d = depth.predict_depth(rgb)
-        return depth.make_sbs(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE)   # D2H float32 HWC + stream sync
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    def timed(fn, steps, **kw):
+    def timed(fn, steps):
+        """`steps` frames through fn (a callable that consumes an iterable of frame indices), device-timed, max over ranks."""
         barrier(); torch.cuda.synchronize()
         s, e = ev(), ev()
         s.record()
-        for i in range(steps):
-            fn(i, **kw)
+        fn(range(steps))
+        torch.cuda.synchronize()
         e.record()
         torch.cuda.synchronize(); barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -242,27 +222,73 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for i in range(warmup):
-        out = step_device(i)
-    assert tuple(out.shape) == (H, 2 * W, 3)
-    torch.cuda.synchronize()
+    def stage_means(trace):
+        torch.cuda.synchronize()
+        st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in trace])
+        return dict(zip(["process", "predict_depth", "warp"], st.mean(0).tolist()))
 
+    # ---- (1) serial, one stream: the drop-in calls back to back; isolates per-stage device times ----
+    serial_trace = []
+
+    def serial_device(idx):
+        for i in idx:
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            rgb = depth.process(frames[i % RING], H)
+            e[1].record()
+            d = depth.predict_depth(rgb)
+            e[2].record()
+            sbs = make_sbs_core(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC")
+            e[3].record()
+            serial_trace.append(e)
+        return sbs
+
+    def serial_e2e(idx):
+        for i in idx:
+            rgb = depth.process(host_np[i % 4], H)            # H2D of the pinned BGRA frame happens here (depth.py:547)
+            d = depth.predict_depth(rgb)
+            out = depth.make_sbs(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE)   # D2H float32 HWC + sync
+        return out
+
+    out = serial_device(range(warmup))
+    assert tuple(out.shape) == (H, 2 * W, 3)
+    serial_trace.clear()
+    n_serial = min(args.steps, 100)
+    ms_serial = timed(serial_device, n_serial)
+    serial_stage_ms = stage_means(serial_trace)
+    serial_e2e(range(warmup))
+    ms_serial_e2e = timed(serial_e2e, n_serial)
+
+    # ---- (2) pipelined: `slots` frames in flight on `slots` CUDA streams (what main.py's 3-thread loop does) ----
+    pipe = StereoPipeline(depth_slots=args.slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO)
+
+    def pipe_device(idx):
+        for _ in pipe.run((frames[i % RING] for i in idx), host=False):
+            pass
+
+    def pipe_e2e(idx):
+        for res in pipe.run((host_np[i % 4] for i in idx), host=True):
+            pass
+        return res
+
+    pipe_device(range(max(warmup, 2 * args.slots)))
+    torch.cuda.synchronize()
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = L.d2s_launch_count()
-    ms = timed(step_device, args.steps, record=True)
+    pipe.trace = []
+    torch.cuda.profiler.start()          # no-op unless run under `ncu --profile-from-start off`
+    ms = timed(pipe_device, args.steps)
+    torch.cuda.profiler.stop()
     launches = L.d2s_launch_count() - launches0
     clk = clocks.stop()
+    stage_ms = stage_means(pipe.trace)   # events recorded on each frame's stream INSIDE the timed region
+    pipe.trace = None
     fps = world * args.steps / (ms / 1e3)
 
-    # per-stage device times from the events recorded inside the timed region
-    torch.cuda.synchronize()
-    st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in stage_ev])
-    stage_ms = dict(zip(["process", "predict_depth", "warp"], st.mean(0).tolist()))
-
-    for i in range(warmup):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    res = pipe_e2e(range(max(warmup, 2 * args.slots)))
+    assert res.shape == (H, 2 * W, 3) and res.dtype == np.float32
+    ms_e2e = timed(pipe_e2e, args.steps)
     fps_e2e = world * args.steps / (ms_e2e / 1e3)
     h2d, d2h = H * W * 4, H * 2 * W * 3 * 4
 
@@ -294,11 +320,15 @@ def main():
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
         "config": {"workload": f"DA-V2-{VARIANT}, 1080p BGRA batch=1 -> {DISPLAY_MODE} (model input 294x518, 778 tokens), per GPU",
-                   "l2": f"ring of {RING} distinct frames ({RING * H * W * 4 / 1e6:.0f} MB) > 126 MB L2", "parallelism": f"frames sharded x{world}",
+                   "l2": f"ring of {RING} distinct frames ({RING * H * W * 4 / 1e6:.0f} MB) > 126 MB L2", "parallelism": f"frames sharded x{world}; {args.slots} frames in flight per GPU",
                    "weights": "seeded random init, one NCCL broadcast at init" if world > 1 else "seeded random init"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "api": "process -> predict_depth -> make_sbs (float32 HWC ndarray out)"},
+                "ms_per_step": ms_e2e / args.steps,
+                "api": f"StereoPipeline({args.slots} frames in flight): pinned BGRA frame -> process -> predict_depth -> make_sbs -> float32 HWC host frame"},
         "gpu_launches": int(launches), "clocks": clk, "stage_ms": stage_ms,
+        "serial": {"note": "same calls, one frame at a time on one stream (latency view)", "steps": n_serial,
+                   "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
+                   "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms},
         "roofline": roofline, "roofline_warp": roofline_warp, "roofline_net": roofline_net,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

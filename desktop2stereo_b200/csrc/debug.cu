@@ -1,9 +1,36 @@
 // Kernel-level entry points used by the parity tests to exercise the tcgen05 GEMM, the implicit-GEMM 3x3 conv and the
 // fused attention in isolation (tests compare each against a plain PyTorch fp32 reference of the same op).
+#include <cstdlib>
+
 #include "gemm.cuh"
 #include "layers.cuh"
 
 using namespace d2s;
+
+// Debug launches own a throw-away scratch for split-K plans (allocated, used, synchronised, freed).
+static int launch_with_scratch(GemmPlan &p, cudaStream_t st) {
+    void *s = nullptr, *c = nullptr;
+    if (p.scratch_bytes) {
+        D2S_CHECK_CUDA(cudaMalloc(&s, p.scratch_bytes)); D2S_CHECK_CUDA(cudaMalloc(&c, p.n_counters * sizeof(unsigned)));
+        D2S_CHECK_CUDA(cudaMemsetAsync(s, 0, p.scratch_bytes, st)); D2S_CHECK_CUDA(cudaMemsetAsync(c, 0, p.n_counters * sizeof(unsigned), st));
+        p.scratch = (float *)s; p.counters = (unsigned *)c;
+    }
+    long long *tr = nullptr;
+    const char *tv = getenv("D2S_GEMM_TRACE");
+    if (tv && tv[0] == '1') { D2S_CHECK_CUDA(cudaMalloc(&tr, 16 * sizeof(long long))); D2S_CHECK_CUDA(cudaMemsetAsync(tr, 0, 16 * sizeof(long long), st)); p.trace = tr; }
+    int rc = gemm_launch(&p, st);
+    if (tr) {
+        long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(tr);
+        fprintf(stderr, "[d2s gemm trace] cycles since entry: setup %lld | first TMA issued %lld | all TMA issued %lld | first full %lld | last MMA committed %lld | "
+                        "epilogue start %lld | epilogue end %lld | after final sync %lld | after dealloc %lld\n",
+                h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0]);
+    }
+    if (s) { cudaStreamSynchronize(st); cudaFree(s); cudaFree(c); }
+    return rc;
+}
 
 extern "C" int d2s_debug_gemm(const void *A, const void *Bw, const float *bias, void *C, int M, int N, int K, int act,
                               float *x32_accumulate, d2s_stream_t stream) {
@@ -12,7 +39,7 @@ extern "C" int d2s_debug_gemm(const void *A, const void *Bw, const float *bias, 
     GemmPlan p;
     int rc = gemm_plan_linear(&p, (const __half *)A, K, (const __half *)Bw, K, M, N, K, e);
     if (rc) return rc;
-    return gemm_launch(&p, (cudaStream_t)stream);
+    return launch_with_scratch(p, (cudaStream_t)stream);
 }
 
 extern "C" int d2s_debug_conv3x3(const void *A, const void *Wt, const float *bias, void *C, int B, int H, int W, int Cp, int N, int act,
@@ -23,7 +50,7 @@ extern "C" int d2s_debug_conv3x3(const void *A, const void *Wt, const float *bia
     GemmPlan p;
     int rc = gemm_plan_conv3x3(&p, (const __half *)A, g, (const __half *)Wt, N, e);
     if (rc) return rc;
-    return gemm_launch(&p, (cudaStream_t)stream);
+    return launch_with_scratch(p, (cudaStream_t)stream);
 }
 
 extern "C" int d2s_debug_attention(const void *qkv, void *out, int B, int N, int D, int heads, d2s_stream_t stream) {

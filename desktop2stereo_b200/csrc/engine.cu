@@ -18,6 +18,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -71,7 +72,8 @@ struct d2s_engine {
     __half *neck_w[4];
     d2s::FusionW fus[4];
     __half *head_c1_w, *head_c2_w; float *head_c1_b, *head_c2_b, *head_c3_w; float head_c3_b;
-    std::map<std::vector<int>, std::unique_ptr<d2s::ShapePlan>> plans;
+    std::map<std::vector<long long>, std::unique_ptr<d2s::ShapePlan>> plans;   // keyed by shape, dtypes AND stream
+    std::mutex mu;
     d2s::ShapePlan *last = nullptr;
     bool use_graph = true;
 };
@@ -199,7 +201,12 @@ static int plan_alloc(ShapePlan *sp, T **p, size_t count) {
     return D2S_OK;
 }
 
-static int add_gemm(ShapePlan *sp, const GemmPlan &gp) {
+static int add_gemm(ShapePlan *sp, GemmPlan gp) {
+    if (gp.scratch_bytes) {   // split-K fix-up scratch: zeroed here once, every launch leaves it zeroed
+        uint8_t *s; unsigned *c;
+        TRY(plan_alloc(sp, &s, gp.scratch_bytes)); TRY(plan_alloc(sp, &c, (size_t)gp.n_counters));
+        gp.scratch = (float *)s; gp.counters = c;
+    }
     sp->ops.push_back([gp](cudaStream_t st) { return gemm_launch(&gp, st); });
     return D2S_OK;
 }
@@ -419,7 +426,10 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
     D2S_REQUIRE(in_dtype == D2S_F32 || in_dtype == D2S_F16, "d2s_infer: pixel_values dtype %d", in_dtype);
     D2S_REQUIRE(out_dtype == D2S_F32 || out_dtype == D2S_F16, "d2s_infer: output dtype %d", out_dtype);
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<int> key = {B, H, W, in_dtype, out_dtype};
+    // One plan (activation buffers + tensor maps + graph) per shape AND per stream: frames submitted on different streams
+    // run concurrently on disjoint buffers while sharing the (read-only) weights.
+    std::vector<long long> key = {B, H, W, in_dtype, out_dtype, (long long)(uintptr_t)stream};
+    std::unique_lock<std::mutex> lock(h->mu);
     auto it = h->plans.find(key);
     if (it == h->plans.end()) {
         // first frame of this shape: allocate buffers, encode tensor maps, capture the graph (the only host-synchronous path,
@@ -442,6 +452,7 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
     }
     ShapePlan *sp = it->second.get();
     h->last = sp;
+    lock.unlock();
     D2S_CHECK_CUDA(cudaMemcpyAsync(sp->in_stage, pixel_values, sp->in_bytes, cudaMemcpyDeviceToDevice, st));
     if (sp->exec) {
         D2S_CHECK_CUDA(cudaGraphLaunch(sp->exec, st));

@@ -5,6 +5,7 @@
 // warps 2..5 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 selects).
 // One 128 x BN output tile per CTA; the ring depth is chosen so two CTAs fit per SM, which overlaps one CTA's
 // epilogue with the other's main loop.
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -21,19 +22,76 @@ struct GemmArgs {
     CUtensorMap tmA, tmB;
     int M, N, kblocks, stages;
     int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y;
+    int splits, kb_per_split;   // split-K: blockIdx.z owns k-blocks [z*kb_per_split, ...)
+    float *scratch;             // fp32 [tiles][128][BN] partial sums (self-cleaning) for the fix-up path
+    unsigned *counters;         // one arrival counter per output tile
+    long long *trace;           // optional: clock64 stamps of CTA (0,0,0) phases (debug)
     GemmEpi epi;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == ACT_GELU) return gelu_erf(v);
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
-    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+    if (ACT == ACT_GELU) return gelu_erf(v);
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
     return v;
 }
 
-template <int BN>
+// Epilogue flavours (compile-time, so that each instantiation's code stays small enough for the instruction cache: the
+// first version carried every flavour behind runtime flags, 88 KB of SASS, and spent ~14k cycles per tile stalled on
+// instruction fetch — profiles/r1_gemm_trace.txt).
+enum { MODE_C16 = 0,    // fp16 store of act(acc + bias) (+ fp16 residuals, + optional relu copy)
+       MODE_X32 = 1,    // fp32 residual stream += acc + bias
+       MODE_HEAD = 2 }; // relu(acc + bias) . w3 + b3 -> final activation -> depth (N <= 32)
+
+// The fused epilogue on 8 consecutive output columns [n, n+8) of one output row (off = row * ldc + n).
+// sb: this tile's bias staged in shared memory (zeros if the GEMM has none); r1/r2: the fp16 residual operands, already
+// loaded by the caller (so that their global-memory round trips overlap instead of forming a chain).
+template <int ACT, int MODE>
+__device__ __forceinline__ void epilogue8(const GemmEpi &e, float (&v)[8], const float *sb, uint4 r1, uint4 r2, long long off, int n,
+                                          float &head_acc) {
+    {
+        float4 b0 = *(const float4 *)sb, b1 = *(const float4 *)(sb + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (ACT != ACT_NONE) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = apply_act<ACT>(v[t]);
+    }
+    if (MODE == MODE_HEAD) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) head_acc = fmaf(v[t], __ldg(e.w3 + n + t), head_acc);
+    } else if (MODE == MODE_X32) {
+        // fire-and-forget reductions into the fp32 stream (no load round trip; one add per element and GEMM when splits == 1)
+        float4 *p = (float4 *)(e.x32 + off);
+        atomicAdd(p, make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(p + 1, make_float4(v[4], v[5], v[6], v[7]));
+    } else {
+        if (e.res1) {
+            const __half2 *h = (const __half2 *)&r1;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
+        }
+        if (e.res2) {
+            const __half2 *h = (const __half2 *)&r2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
+        }
+        __half2 h[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+        *(uint4 *)(e.c16 + off) = *(const uint4 *)h;
+        if (e.c16_relu) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __hmax2(h[t], __float2half2_rn(0.f));
+            *(uint4 *)(e.c16_relu + off) = *(const uint4 *)h;
+        }
+    }
+}
+
+template <int BN, int ACT, int MODE>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int kBBytes = BN * BK * 2;
@@ -44,9 +102,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     uint64_t *empty = full + stages;
     uint64_t *tmem_full = empty + stages;
     uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    volatile uint32_t *flag = tmem_slot + 1;   // split-K: "this CTA arrived last"
+    float *s_bias = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);  // this tile's bias (BN floats), staged by the epilogue warps during the main loop
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const bool tr = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define D2S_STAMP(i) do { if (tr) g.trace[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) D2S_STAMP(0);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&g.tmA);
@@ -64,6 +127,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) D2S_STAMP(1);
 
     // conv tile -> (image, y0, x0)
     int img = 0, y0 = 0, x0 = 0;
@@ -75,44 +139,57 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         x0 = (t % g.tiles_x) * g.TW;
     }
 
+    // split-K range of this CTA
+    const int kb0 = blockIdx.z * g.kb_per_split;
+    const int nkb = min(kb0 + g.kb_per_split, g.kblocks) - kb0;
+
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
             const int cchunks = g.conv ? (g.Cp / BK) : 1;
-            for (int kb = 0; kb < g.kblocks; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                ptx::mbar_wait(&empty[s], ph ^ 1);
-                uint8_t *a = smem + (size_t)s * kStageBytes, *b = a + kABytes;
+            int tap = kb0 / cchunks, cc = kb0 - tap * cchunks;   // conv: k-block -> (filter tap, channel chunk)
+            int s = 0;
+            uint32_t ph = 0;
+            uint8_t *a = smem;
+            for (int i = 0; i < nkb; ++i) {
+                if (i >= stages) ptx::mbar_wait(&empty[s], ph ^ 1);   // the first pass over the ring finds every slot free
                 ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
                 if (g.conv) {
-                    int tap = kb / cchunks, cc = kb - tap * cchunks;
-                    int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
                     ptx::tma_load_4d(a, &g.tmA, &full[s], cc * BK, x0 + dx, y0 + dy, img);
+                    if (++cc == cchunks) { cc = 0; ++tap; }
                 } else {
-                    ptx::tma_load_2d(a, &g.tmA, &full[s], kb * BK, tile_m * BM);
+                    ptx::tma_load_2d(a, &g.tmA, &full[s], (kb0 + i) * BK, tile_m * BM);
                 }
-                ptx::tma_load_2d(b, &g.tmB, &full[s], kb * BK, tile_n * BN);
+                ptx::tma_load_2d(a + kABytes, &g.tmB, &full[s], (kb0 + i) * BK, tile_n * BN);
+                if (i == 0) D2S_STAMP(2);
+                a += kStageBytes;
+                if (++s == stages) { s = 0; ph ^= 1; a = smem; }
             }
+            D2S_STAMP(3);
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t idesc = ptx::make_idesc_f16(BM, BN, 0);
-            for (int kb = 0; kb < g.kblocks; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
+            int s = 0;
+            uint32_t ph = 0;
+            uint32_t a_addr = ptx::smem_u32(smem);
+            for (int i = 0; i < nkb; ++i) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * kStageBytes);
+                if (i == 0) D2S_STAMP(4);
                 const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr);
                 const uint64_t db = ptx::make_sw128_kmajor_desc(a_addr + kABytes);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 bytes: advance the start address by 2 (>>4)
-                    ptx::umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    ptx::umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
                 ptx::umma_commit(&empty[s]);  // smem slot is free once these MMAs have read it
+                a_addr += kStageBytes;
+                if (++s == stages) { s = 0; ph ^= 1; a_addr = ptx::smem_u32(smem); }
             }
             ptx::umma_commit(tmem_full);      // accumulator complete
+            D2S_STAMP(5);
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
@@ -127,84 +204,115 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
             int m = tile_m * BM + r;
             orow = m < g.M ? m : -1;
         }
+        // stage the bias while the main loop runs (the epilogue warps have nothing else to do yet)
+        {
+            const int t = threadIdx.x - 64, n = tile_n * BN + t;
+            if (t < BN) s_bias[t] = (e.bias && n < g.N && (MODE != MODE_X32 || blockIdx.z == 0)) ? __ldg(e.bias + n) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // split-K flavours: (a) MODE_X32 -> every split adds its partial to the fp32 stream (bias from split 0 only);
+        // (b) anything else -> partials meet in an fp32 scratch tile, the last-arriving CTA runs the real epilogue.
+        const bool fixup = g.splits > 1 && MODE != MODE_X32;
+        const bool has_res = MODE == MODE_C16 && (e.res1 || e.res2);
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
+        if (threadIdx.x == 64) D2S_STAMP(6);
         float head_acc = 0.f;
+        if (!fixup) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t raw[32];
-            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-            ptx::tmem_ld_wait();
-            const int n0 = tile_n * BN + c * 32;
-            if (orow < 0 || n0 >= g.N) continue;
-            const long long off = orow * e.ldc + n0;
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+                const int n0 = tile_n * BN + c * 32;
+                const bool live = orow >= 0 && n0 < g.N;
+                const long long off0 = orow * e.ldc + n0;
+                uint4 r1[4] = {z4, z4, z4, z4}, r2[4] = {z4, z4, z4, z4};
+                if (has_res && live) {   // all residual loads of this chunk in flight together, under the TMEM load
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                if (n0 + j >= g.N) break;      // N is a multiple of 8
-                float v[8];
+                    for (int j = 0; j < 4; ++j)
+                        if (n0 + j * 8 < g.N) {
+                            if (e.res1) r1[j] = __ldg((const uint4 *)(e.res1 + off0 + j * 8));
+                            if (e.res2) r2[j] = __ldg((const uint4 *)(e.res2 + off0 + j * 8));
+                        }
+                }
+                ptx::tmem_ld_wait();
+                if (!live) continue;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(raw[j + t]);
-                if (e.bias) {
-                    float4 b0 = __ldg((const float4 *)(e.bias + n0 + j)), b1 = __ldg((const float4 *)(e.bias + n0 + j + 4));
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (e.act != ACT_NONE) {
+                for (int j = 0; j < 4; ++j) {
+                    if (n0 + j * 8 >= g.N) break;      // N is a multiple of 8
+                    float v[8];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) v[t] = apply_act(v[t], e.act);
-                }
-                if (e.res1) {
-                    uint4 u = __ldg((const uint4 *)(e.res1 + off + j));
-                    const __half2 *h = (const __half2 *)&u;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
-                }
-                if (e.res2) {
-                    uint4 u = __ldg((const uint4 *)(e.res2 + off + j));
-                    const __half2 *h = (const __half2 *)&u;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
-                }
-                if (e.w3) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) head_acc = fmaf(v[t], __ldg(e.w3 + n0 + j + t), head_acc);
-                }
-                if (e.x32) {
-                    float4 *p = (float4 *)(e.x32 + off + j);
-                    float4 a = p[0], b = p[1];
-                    a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3]; b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
-                    p[0] = a; p[1] = b;
-                }
-                if (e.c32) {
-                    float4 *p = (float4 *)(e.c32 + off + j);
-                    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    p[1] = make_float4(v[4], v[5], v[6], v[7]);
-                }
-                if (e.c16) {
-                    __half2 h[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-                    *(uint4 *)(e.c16 + off + j) = *(const uint4 *)h;
-                }
-                if (e.c16_relu) {
-                    __half2 h[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(fmaxf(v[2 * t], 0.f), fmaxf(v[2 * t + 1], 0.f));
-                    *(uint4 *)(e.c16_relu + off + j) = *(const uint4 *)h;
+                    for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(raw[j * 8 + t]);
+                    epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
                 }
             }
+        } else {
+            // (b) accumulate this split's partial tile
+            float *tile = g.scratch + ((size_t)tile_m * gridDim.x + tile_n) * (size_t)(BM * BN) + (size_t)r * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    atomicAdd((float4 *)(tile + c * 32 + j), make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                                         __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+            unsigned *ctr = g.counters + (size_t)tile_m * gridDim.x + tile_n;
+            if (threadIdx.x == 64) *flag = (atomicAdd(ctr, 1u) == (unsigned)(g.splits - 1)) ? 1u : 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*flag) {                                               // last CTA of this tile: full sums are in scratch
+                __threadfence();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int n0 = tile_n * BN + c * 32;
+                    const bool live = orow >= 0 && n0 < g.N;
+                    const long long off0 = orow * e.ldc + n0;
+                    float4 acc[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = __ldcg((const float4 *)(tile + c * 32 + j * 4));
+                    uint4 r1[4] = {z4, z4, z4, z4}, r2[4] = {z4, z4, z4, z4};
+                    if (has_res && live) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (n0 + j * 8 < g.N) {
+                                if (e.res1) r1[j] = __ldg((const uint4 *)(e.res1 + off0 + j * 8));
+                                if (e.res2) r2[j] = __ldg((const uint4 *)(e.res2 + off0 + j * 8));
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcg((float4 *)(tile + c * 32 + j * 4), make_float4(0.f, 0.f, 0.f, 0.f));  // leave it clean
+                    if (!live) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (n0 + j * 8 >= g.N) break;
+                        float v[8] = {acc[2 * j].x, acc[2 * j].y, acc[2 * j].z, acc[2 * j].w, acc[2 * j + 1].x, acc[2 * j + 1].y, acc[2 * j + 1].z, acc[2 * j + 1].w};
+                        epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
+                    }
+                }
+                if (threadIdx.x == 64) *ctr = 0u;
+            }
         }
-        if (e.w3 && orow >= 0 && tile_n == 0) {
-            float d = apply_act(head_acc + e.b3, e.final_act) * e.max_depth;
+        if (MODE == MODE_HEAD && orow >= 0 && tile_n == 0 && (!fixup || *flag)) {
+            float d = (e.final_act == ACT_SIGMOID ? apply_act<ACT_SIGMOID>(head_acc + e.b3) : fmaxf(head_acc + e.b3, 0.f)) * e.max_depth;
             if (e.depth_dtype == D2S_F16) ((__half *)e.depth_out)[orow] = __float2half_rn(d);
             else ((float *)e.depth_out)[orow] = d;
         }
+        if (threadIdx.x == 64) D2S_STAMP(7);
         ptx::tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) D2S_STAMP(8);
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, BN);
     }
+    if (threadIdx.x == 32) D2S_STAMP(9);
+#undef D2S_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,11 +322,24 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+
+// the instantiations the network needs: (BN, activation, epilogue mode)
+typedef void (*GemmKernel)(const GemmArgs);
+struct Variant { int bn, act, mode; GemmKernel fn; };
+#define D2S_V(bn, act, mode) {bn, act, mode, gemm_tc_kernel<bn, act, mode>}
+static const Variant kVariants[] = {
+    D2S_V(128, ACT_NONE, MODE_C16), D2S_V(128, ACT_RELU, MODE_C16), D2S_V(128, ACT_GELU, MODE_C16), D2S_V(128, ACT_NONE, MODE_X32),
+    D2S_V(64, ACT_NONE, MODE_C16),  D2S_V(64, ACT_RELU, MODE_C16),  D2S_V(64, ACT_GELU, MODE_C16),  D2S_V(64, ACT_NONE, MODE_X32),
+    D2S_V(32, ACT_NONE, MODE_C16),  D2S_V(32, ACT_RELU, MODE_C16),  D2S_V(32, ACT_RELU, MODE_HEAD), D2S_V(32, ACT_NONE, MODE_X32),
+};
+#undef D2S_V
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+static int epi_mode(const GemmEpi &e) { return e.w3 ? MODE_HEAD : (e.x32 ? MODE_X32 : MODE_C16); }
 static std::once_flag g_once;
 static int g_init_rc = D2S_OK;
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int BN> static size_t smem_for(int stages) { return (size_t)stages * (kABytes + BN * BK * 2) + (2 * stages + 1) * 8 + 16 + 1024; }
+template <int BN> static size_t smem_for(int stages) { return (size_t)stages * (kABytes + BN * BK * 2) + (2 * stages + 1) * 8 + 32 + 512 + 1024; }
 
 int gemm_init() {
     std::call_once(g_once, [] {
@@ -230,9 +351,9 @@ int gemm_init() {
             return;
         }
         g_encode = (EncodeTiledFn)fn;
-        cudaError_t a = cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        cudaError_t a = cudaSuccess;
+        for (int i = 0; i < kNumVariants && a == cudaSuccess; ++i)
+            a = cudaFuncSetAttribute((const void *)kVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
         if (a != cudaSuccess) g_init_rc = set_error(D2S_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(a));
     });
     return g_init_rc;
@@ -265,21 +386,57 @@ static int encode_nhwc(CUtensorMap *m, const void *base, const ConvGeom &g, int 
 
 static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
 
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Choose the split-K factor and the ring depth.  Most of this network's GEMMs are small (M = 778 tokens, or a few
+// hundred pixels at the coarse DPT levels): with one 128 x BN tile per CTA the grid covers a fraction of the 148 SMs and
+// the kernel time is a serial chain of k-blocks, each bounded by TMA latency / ring depth.  So: split K until the grid
+// fills one wave, and make the ring as deep as the chain (one CTA per SM) unless the grid needs two CTAs per SM.
 static void finish_plan(GemmPlan *p) {
-    // ring depth: as deep as useful while leaving room for two CTAs per SM
-    size_t stage = kABytes + (size_t)p->BN * BK * 2;
-    int stages = (int)((kMaxSmem / 2 - 2048) / stage);
-    if (stages > p->kblocks) stages = p->kblocks;
+    const int base = p->grid.x * p->grid.y;
+    const GemmEpi &e = p->epi;
+    const bool atomic_ok = epi_mode(e) == MODE_X32;
+    int splits = 1;
+    const int max_splits = env_int("D2S_GEMM_MAX_SPLITS", 16);
+    if (atomic_ok) {
+        splits = kNumSMs / base;                       // atomics into the fp32 stream: splitting is free
+        if (splits > p->kblocks / 3) splits = p->kblocks / 3;
+    } else if (base * 2 <= kNumSMs && p->kblocks >= 16) {
+        splits = kNumSMs / base;                       // fix-up path: only when the chain is long and the grid small
+        if (splits > p->kblocks / 4) splits = p->kblocks / 4;
+    }
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p->kb_per_split = ceil_div(p->kblocks, splits);
+    p->splits = ceil_div(p->kblocks, p->kb_per_split);   // no empty split
+    p->grid.z = p->splits;
+    p->scratch_bytes = (p->splits > 1 && !atomic_ok) ? (size_t)base * BM * p->BN * sizeof(float) : 0;
+    p->n_counters = (p->splits > 1 && !atomic_ok) ? base : 0;
+
+    const size_t stage = kABytes + (size_t)p->BN * BK * 2;
+    const size_t budget = (base * p->splits > kNumSMs) ? kMaxSmem / 2 : kMaxSmem;   // two CTAs per SM only if needed
+    int stages = (int)((budget - 2048) / stage);
+    if (stages > p->kb_per_split) stages = p->kb_per_split;
     if (stages < 2) stages = 2;
-    if (stages > 8) stages = 8;
+    if (stages > 12) stages = 12;
     p->stages = stages;
-    p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 16 + 1024;
+    p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 32 + 512 + 1024;
+    if (env_int("D2S_VERBOSE", 0))
+        fprintf(stderr, "[d2s gemm] %s M=%d N=%d K=%d BN=%d grid=(%d,%d,%d) kblocks=%d kb/split=%d stages=%d smem=%zu %s\n", p->conv ? "conv" : "lin ",
+                p->M, p->N, p->K, p->BN, p->grid.x, p->grid.y, p->grid.z, p->kblocks, p->kb_per_split, stages, p->smem,
+                p->splits > 1 ? (atomic_ok ? "split:atomic" : "split:fixup") : "");
 }
 
 static int check_epi(const GemmEpi &e, int N) {
     D2S_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
     D2S_REQUIRE(e.ldc % 8 == 0 || !(e.c16 || e.c16_relu || e.res1 || e.res2 || e.x32 || e.c32), "gemm: ldc=%d must be a multiple of 8", e.ldc);
     D2S_REQUIRE(!e.w3 || N <= 32, "gemm: fused 1x1 head needs N <= 32 (got %d)", N);
+    D2S_REQUIRE(!e.x32 || !(e.c16 || e.c16_relu || e.res1 || e.res2 || e.w3 || e.act != ACT_NONE), "gemm: the fp32-stream epilogue takes bias only");
+    D2S_REQUIRE(e.x32 || e.w3 || e.c16, "gemm: no output");
+    D2S_REQUIRE(!e.c32, "gemm: fp32 plain-store epilogue was removed");
     return D2S_OK;
 }
 
@@ -323,12 +480,16 @@ int gemm_launch(const GemmPlan *p, cudaStream_t stream) {
     a.M = p->M; a.N = p->N; a.kblocks = p->kblocks; a.stages = p->stages;
     a.conv = p->conv; a.H = p->H; a.W = p->W; a.Cp = p->Cp; a.TW = p->TW; a.TW_shift = p->TW == 8 ? 3 : 4;
     a.tiles_x = p->tiles_x; a.tiles_y = p->tiles_y;
+    a.trace = p->trace;
+    a.splits = p->splits; a.kb_per_split = p->kb_per_split; a.scratch = p->scratch; a.counters = p->counters;
+    if (p->scratch_bytes && (!p->scratch || !p->counters)) return set_error(D2S_ERR_INVALID, "gemm: split-K plan without scratch");
     a.epi = p->epi;
-    switch (p->BN) {
-        case 32: D2S_LAUNCH(gemm_tc_kernel<32>, p->grid, kGemmThreads, p->smem, stream, a); break;
-        case 64: D2S_LAUNCH(gemm_tc_kernel<64>, p->grid, kGemmThreads, p->smem, stream, a); break;
-        default: D2S_LAUNCH(gemm_tc_kernel<128>, p->grid, kGemmThreads, p->smem, stream, a); break;
-    }
+    const int mode = epi_mode(p->epi);
+    GemmKernel fn = nullptr;
+    for (int i = 0; i < kNumVariants; ++i)
+        if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode) fn = kVariants[i].fn;
+    if (!fn) return set_error(D2S_ERR_UNSUPPORTED, "gemm: no kernel variant for BN=%d act=%d mode=%d", p->BN, p->epi.act, mode);
+    D2S_LAUNCH(fn, p->grid, kGemmThreads, p->smem, stream, a);
     D2S_POST_LAUNCH();
     return D2S_OK;
 }

@@ -42,6 +42,12 @@ struct GemmPlan {  // everything a launch needs; built once per shape, replayed 
     int conv;             // 0 linear, 1 implicit 3x3
     int H, W, Cp, TH, TW, tiles_x, tiles_y, B;
     int kblocks;
+    int splits, kb_per_split;      // split-K (grid.z)
+    size_t scratch_bytes;          // fix-up path: fp32 scratch the caller must provide ZEROED (it is left zeroed)
+    int n_counters;                // ... and this many zeroed unsigned counters
+    float *scratch;
+    unsigned *counters;
+    long long *trace;              // debug: clock64 stamps of CTA (0,0,0)
     GemmEpi epi;
     dim3 grid;
     size_t smem;

@@ -54,7 +54,7 @@ _ws_cache: dict = {}
 
 
 def _workspace(dev, nbytes: int, tag: str) -> torch.Tensor:
-    key = (dev, tag)
+    key = (dev, tag, _stream_ptr(dev))   # per stream: concurrent frames must not share scratch
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = _ws_cache[key] = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
@@ -118,13 +118,22 @@ class PostProcessor:
         p.compute_dtype, p.metric = _TORCH2D2S[cdt], int(self.metric)
         p.percentile, p.subsample_cap, p.gamma = self.percentile, self.subsample_cap, self.gamma
         p.foreground_scale, p.aa_strength = self.foreground_scale, self.aa_strength
+        cur = torch.cuda.current_stream(dev)
         if use_temporal_smooth:
             if self.prev is None or self.prev.shape != (H, W) or self.prev.device != dev or self.prev.dtype != cdt:
                 self.prev, self.prev_valid = torch.empty((H, W), dtype=cdt, device=dev), False
+                self._ema_event = None
             p.ema_state, p.ema_valid, p.ema_alpha = self.prev.data_ptr(), int(self.prev_valid), self.ema_alpha
             self.prev_valid = True
+            # frames of one video stream may be in flight on several CUDA streams: the EMA is the one cross-frame
+            # dependency of the path (depth.py:1865-1887), so frame t's update is ordered after frame t-1's
+            if getattr(self, "_ema_event", None) is not None:
+                cur.wait_event(self._ema_event)
         p.out_lowres = low.data_ptr() if low is not None else None
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(dev):
-            _lib.check(L.d2s_postprocess(C.byref(p), _stream_ptr(dev)), "d2s_postprocess")
+            _lib.check(L.d2s_postprocess(C.byref(p), cur.cuda_stream), "d2s_postprocess")
+        if use_temporal_smooth:
+            self._ema_event = torch.cuda.Event()
+            self._ema_event.record(cur)
         return (out, low) if return_lowres else out

@@ -47,9 +47,24 @@ def test_engine_vs_golden_and_oracle(cuda_device, golden_dir, case):
     assert report["hidden_last"] <= 2e-3, report
     assert report["depth_vs_oracle"] <= 5e-3, report
     assert report["depth_vs_golden"] <= 5e-3, report
-    # replay (CUDA graph) is deterministic and fp16 output is the rounded fp32 output
-    assert torch.equal(eng(x), out)
-    assert torch.equal(eng(x, out_dtype=torch.float16), out.half())
+    # replay (CUDA graph): split-K partial sums meet through fp32 atomics, so two runs differ by accumulation-order noise,
+    # which can flip the fp16 rounding of an intermediate activation: max-norm agreement is one fp16 ulp-ish, mean far lower
+    again = eng(x)
+    assert _rel(again, out) <= 3e-3 and (again - out).abs().mean().item() <= 2e-4 * out.abs().max().item()
+    assert _rel(eng(x, out_dtype=torch.float16).float(), out) <= 4e-3
+    eng.close()
+
+
+def test_engine_deterministic_mode(cuda_device, monkeypatch):
+    """D2S_GEMM_MAX_SPLITS=1 disables split-K: replays are then bit-identical."""
+    from desktop2stereo_b200.engine import B200Engine
+    from oracle.gen_golden import TINY
+    monkeypatch.setenv("D2S_GEMM_MAX_SPLITS", "1")
+    eng = B200Engine.from_hf_model(make_hf_model("Small", 3, TINY), cuda_device, out_dtype=torch.float32)
+    x = torch.from_numpy(model_input(3, 2, 70, 98)).to(cuda_device)
+    a = eng(x).clone()
+    for _ in range(3):
+        assert torch.equal(eng(x), a)
     eng.close()
 
 
