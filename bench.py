@@ -175,23 +175,17 @@ def main():
     warmup = max(args.warmup, 3)
 
     # ---- weights: rank 0 packs, one NCCL broadcast over NVLink, every rank builds its own engine ----
-    from transformers import DepthAnythingConfig  # config only on ranks > 0
+    from transformers import DepthAnythingConfig
+    from desktop2stereo_b200 import sharding
+    blob = cfg_json = None
     if rank == 0:
         model = build_hf_model()
-        cfg = config_from_hf(model.config)
-        blob = torch.from_numpy(pack_state_dict(model.state_dict(), cfg))
-        hf_cfg_json = model.config.to_json_string()
+        blob = pack_state_dict(model.state_dict(), config_from_hf(model.config))
+        cfg_json = model.config.to_json_string()
         del model
-    if world > 1:
-        meta = [hf_cfg_json, blob.numel()] if rank == 0 else [None, None]
-        dist.broadcast_object_list(meta, src=0)
-        if rank != 0:
-            cfg = config_from_hf(DepthAnythingConfig.from_dict(json.loads(meta[0])))
-        dblob = blob.to(dev) if rank == 0 else torch.empty(meta[1], dtype=torch.float32, device=dev)
-        dist.broadcast(dblob, src=0)
-        blob = dblob.cpu()
-        del dblob
-    engine = B200Engine(blob.numpy(), cfg, dev, out_dtype=torch.float16)
+    blob, cfg_json = sharding.broadcast_weights(blob, cfg_json, src=0, device=dev)
+    cfg = config_from_hf(DepthAnythingConfig.from_dict(json.loads(cfg_json)))
+    engine = B200Engine(blob, cfg, dev, out_dtype=torch.float16)
     depth.init(engine=engine, device=dev)
 
     # ---- synthetic frames: a ring larger than L2 so no timed iteration re-reads a cached frame ----

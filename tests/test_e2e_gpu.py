@@ -54,7 +54,8 @@ def test_temporal_smoothing_state(cuda_device):
     depth.depth_stabilizer.reset()
     b0 = depth.predict_depth(depth.process(f0, 90))
     b1 = depth.predict_depth(depth.process(f1, 90))
-    assert torch.equal(a0, b0)
+    # first frame passes through the stabiliser unchanged (split-K atomics make two runs agree to fp16-ulp noise, not bitwise)
+    assert (a0.float() - b0.float()).abs().max().item() <= 3e-3
     mix = 0.9 * a0.float() + 0.1 * a1.float()
     assert (b1.float() - mix).abs().max().item() <= 3e-3     # EMA runs on the low-res fp16 map before the upsample
     assert not torch.equal(a1, b1)
