@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
-    ap.add_argument("--slots", type=int, default=3, help="frames in flight (CUDA streams) in the pipelined legs")
+    ap.add_argument("--slots", type=int, default=4, help="frames in flight (CUDA streams) in the pipelined legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -422,6 +422,7 @@ static void finish_plan(GemmPlan *p) {
     if (stages > p->kb_per_split) stages = p->kb_per_split;
     if (stages < 2) stages = 2;
     if (stages > 12) stages = 12;
+    { int ms = env_int("D2S_GEMM_MAX_STAGES", 0); if (ms >= 2 && stages > ms) stages = ms; }
     p->stages = stages;
     p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 32 + 512 + 1024;
     if (env_int("D2S_VERBOSE", 0))

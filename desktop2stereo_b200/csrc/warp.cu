@@ -12,6 +12,8 @@
 // materialises shifts, two [h,w,2] fp32 grids, two eye images, the concatenation and the pooled copy
 // (~10x the algorithmic bytes); here each source byte is read from HBM once and each
 // output byte written once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace d2s {
@@ -33,17 +35,20 @@ __device__ __forceinline__ float linspace_pm1(int i, int n, float step, int half
     return (i < half) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(n - i - 1), 1.0f);
 }
 
+// reflect_coordinates for |coord| >= span (rare: only within |shift| of the right border); fmod/floor/div are exact here.
+__device__ __noinline__ float reflect_slow(float in, float span) {
+    float extra = fmodf(in, span);
+    int flips = (int)floorf(__fdiv_rn(in, span));
+    return (flips % 2 == 0) ? extra : __fsub_rn(span, extra);
+}
+
 // grid_sampler_compute_source_index, padding_mode=reflection, align_corners=True (GridSampler.cuh)
 __device__ __forceinline__ float source_index(float coord, int size) {
     coord = __fmul_rn(__fmul_rn(__fadd_rn(coord, 1.f), 0.5f), (float)(size - 1));
     if (size == 1) return 0.f;
     const float span = (float)(size - 1);
     float in = fabsf(coord);
-    if (in >= span) {  // rare: only within |shift| of the right border.  fmod/floor/div are exact here.
-        float extra = fmodf(in, span);
-        int flips = (int)floorf(__fdiv_rn(in, span));
-        in = (flips % 2 == 0) ? extra : __fsub_rn(span, extra);
-    }
+    if (in >= span) in = reflect_slow(in, span);
     // in < span: fmod(in,span)==in and floor(in/span)==0 exactly, so reflect_coordinates returns `in`.
     return fminf(span, fmaxf(in, 0.f));
 }
@@ -68,9 +73,18 @@ __device__ __forceinline__ RowCtx make_row(const WarpK &k, int y) {
 // depth at full-res pixel (y,x) in the value set of DT.  lowres: upsample_bilinear2d (align_corners=False),
 // restated from ATen's CUDA kernel (UpSampleBilinear2d.cu): accumulate in fp32, round to DT.
 template <typename DT>
+__device__ __noinline__ float load_depth_lowres(const WarpK &k, int y, int x);
+
+template <typename DT>
 __device__ __forceinline__ float load_depth(const WarpK &k, int y, int x) {
     const DT *d = (const DT *)k.depth;
     if (!k.lowres) return to_f32<DT>(__ldg(d + (size_t)y * k.w + x));
+    return load_depth_lowres<DT>(k, y, x);
+}
+
+template <typename DT>
+__device__ __noinline__ float load_depth_lowres(const WarpK &k, int y, int x) {
+    const DT *d = (const DT *)k.depth;
     float h1r = fmaxf(__fmaf_rn(k.dscale_h, (float)y + 0.5f, -0.5f), 0.f);
     float w1r = fmaxf(__fmaf_rn(k.dscale_w, (float)x + 0.5f, -0.5f), 0.f);
     int h1 = (int)h1r, w1 = (int)w1r;
@@ -227,6 +241,144 @@ __global__ void __launch_bounds__(256) warp_sbs_kernel(const WarpK k) {
     store_px4<OT>(k, oy, ox0, n, v);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path (bilinear branch, no 16:9 padding, Full-SBS / Full-TAB / Half-SBS): source-centric.
+// One block = one source row segment.  The rgb row(s) the segment can reach (|shift| is bounded by the parameters for
+// depth in [0,1]) are staged once in shared memory as fp32 planes with coalesced loads; each thread then owns NP
+// consecutive source pixels, reads their depth once, runs the shift chain once and produces BOTH eyes from smem taps.
+// Same arithmetic, same FMA order as the generic kernel => bit-identical output (tests compare both against the oracle).
+// ------------------------------------------------------------------------------------------------
+// the taps of one eye pixel straight from global memory (fast kernel: the tap left the staged window, i.e. depth outside [0,1])
+template <typename RT, typename DT>
+__device__ __noinline__ float3 taps_global(const WarpK &k, int iy0, bool two, int ix0, float nw, float ne, float sw, float se) {
+    const bool okx1 = ix0 + 1 < k.w;
+    float o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0, ix0), nw, 0.f);
+        if (okx1) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0, ix0 + 1), ne, acc);
+        if (two) {
+            acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0 + 1, ix0), sw, acc);
+            if (okx1) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0 + 1, ix0 + 1), se, acc);
+        }
+        o[ch] = acc;
+    }
+    return make_float3(o[0], o[1], o[2]);
+}
+
+constexpr int kFastThreads = 128;
+
+// One warped eye pixel from the staged rows.  Same arithmetic and FMA order as eye_pixel().
+template <typename RT, typename DT>
+__device__ __forceinline__ float3 eye_from_smem(const WarpK &k, const RowCtx &row, bool two, const float *s0, const float *s1, int tw,
+                                                int lo, int hi, float gx) {
+    const float ix = source_index(gx, k.w);
+    const int ix0 = __float2int_rz(ix);   // ix >= 0 after the clip: truncation == floor
+    const float wx0 = __fsub_rn((float)(ix0 + 1), ix), wx1 = __fsub_rn(ix, (float)ix0);
+    const float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
+    const float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
+    const bool okx1 = ix0 + 1 < k.w;
+    const int a = ix0 - lo;
+    if (a < 0 || ix0 + (okx1 ? 1 : 0) >= hi) return taps_global<RT, DT>(k, row.iy0, two, ix0, nw, ne, sw, se);
+    const int b = okx1 ? a + 1 : a;       // when !okx1 the NE/SE taps are skipped, exactly like the bounds check of grid_sample
+    float o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float acc = __fmaf_rn(s0[ch * tw + a], nw, 0.f);
+        if (okx1) acc = __fmaf_rn(s0[ch * tw + b], ne, acc);
+        if (two) {
+            acc = __fmaf_rn(s1[ch * tw + a], sw, acc);
+            if (okx1) acc = __fmaf_rn(s1[ch * tw + b], se, acc);
+        }
+        o[ch] = acc;
+    }
+    return make_float3(o[0], o[1], o[2]);
+}
+
+// OL: output layout known at compile time — 0: HWC contiguous (sx = 3, sc = 1), 1: planar CHW (sx = 1)
+template <typename RT, typename DT, typename OT, int HALF, int OL>
+__global__ void __launch_bounds__(kFastThreads) warp_sbs_fast_kernel(const WarpK k, int margin) {
+    typedef typename Vec4<OT>::type V;
+    constexpr int NP = HALF ? 8 : 4;                 // source pixels per thread
+    constexpr int SEG = kFastThreads * NP;           // source pixels per block
+    extern __shared__ float s_rgb[];                 // [rows(1|2)][3][tw]
+    const int y = blockIdx.y;
+    const int seg0 = blockIdx.x * SEG;
+    const int lo = max(seg0 - margin, 0), hi = min(seg0 + SEG + margin, k.w);   // staged source columns [lo, hi)
+    const int tw = hi - lo;
+    const RowCtx row = make_row(k, y);
+    const bool two = row.ok1 && row.wy1 != 0.f;      // second source row contributes (block-uniform)
+    const int nrows = two ? 2 : 1;
+    for (int r = 0; r < nrows; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float *dst = s_rgb + (r * 3 + c) * tw;
+            const RT *src = (const RT *)k.rgb + c * k.rsc + (long long)(row.iy0 + r) * k.rsy + (long long)lo * k.rsx;
+            for (int x = threadIdx.x; x < tw; x += kFastThreads) {
+                float v = to_f32<RT>(__ldg(src + (long long)x * k.rsx));
+                if (sizeof(RT) != 1) {
+                    if (k.rgb_round) v = round_to<DT>(v);
+                    v = fminf(fmaxf(v, 0.f), 255.f);
+                }
+                dst[x] = v;
+            }
+        }
+    __syncthreads();
+    const int x0 = seg0 + threadIdx.x * NP;
+    if (x0 >= k.w) return;
+    const float *s0 = s_rgb, *s1 = s_rgb + 3 * tw;
+    const int npx = min(NP, k.w - x0);               // < NP only for the last thread of a row
+
+    float3 eye[2][NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int x = min(x0 + p, k.w - 1);          // clamped duplicates are computed but never stored
+        // shift chain, depth.py:2143-2147, :2154 (identical to eye_pixel)
+        float d = round_to<DT>(__fsub_rn(load_depth<DT>(k, y, x), k.conv));
+        float inv = round_to<DT>(__fmul_rn(-d, k.ratio));
+        float s = round_to<DT>(__fmul_rn(inv, k.max_px));
+        s = round_to<DT>(__fmul_rn(s, k.strength));
+        const float sn = round_to<DT>(__fmul_rn(s, k.two_over_wm1));
+        const float xs = linspace_pm1(x, k.w, k.xstep, k.xhalf);
+        eye[0][p] = eye_from_smem<RT, DT>(k, row, two, s0, s1, tw, lo, hi, __fadd_rn(xs, sn));
+        eye[1][p] = eye_from_smem<RT, DT>(k, row, two, s0, s1, tw, lo, hi, __fsub_rn(xs, sn));
+    }
+    // pack: Full modes 4 px per eye; Half-SBS: 8 source px -> 4 pair-means per eye; final clamp (depth.py:2184)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        float v[4][3];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float3 a = HALF ? make_float3(__fmul_rn(__fadd_rn(eye[e][2 * p].x, eye[e][2 * p + 1].x), 0.5f),
+                                          __fmul_rn(__fadd_rn(eye[e][2 * p].y, eye[e][2 * p + 1].y), 0.5f),
+                                          __fmul_rn(__fadd_rn(eye[e][2 * p].z, eye[e][2 * p + 1].z), 0.5f))
+                            : eye[e][p];
+            v[p][0] = fminf(fmaxf(a.x, 0.f), 255.f); v[p][1] = fminf(fmaxf(a.y, 0.f), 255.f); v[p][2] = fminf(fmaxf(a.z, 0.f), 255.f);
+        }
+        const int oy = k.tab ? e * k.h + y : y;
+        const int ox = (k.tab ? 0 : e * (HALF ? k.w / 2 : k.w)) + (HALF ? x0 / 2 : x0);
+        const int valid = HALF ? npx / 2 : npx;
+        OT *base = (OT *)k.out + (long long)oy * k.osy + (long long)ox * (OL == 0 ? 3 : 1);
+        if (valid == 4 && ((uintptr_t)base % sizeof(V)) == 0 && (OL == 0 || (k.osc * (long long)sizeof(OT)) % sizeof(V) == 0)) {
+            if (OL == 0) {
+                V *dv = (V *)base;
+                dv[0] = Vec4<OT>::pack(v[0][0], v[0][1], v[0][2], v[1][0]);
+                dv[1] = Vec4<OT>::pack(v[1][1], v[1][2], v[2][0], v[2][1]);
+                dv[2] = Vec4<OT>::pack(v[2][2], v[3][0], v[3][1], v[3][2]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) *(V *)(base + c * k.osc) = Vec4<OT>::pack(v[0][c], v[1][c], v[2][c], v[3][c]);
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < valid * 3; ++i) {
+                int pp = i / 3, c = i - pp * 3;
+                base[OL == 0 ? i : c * k.osc + pp] = from_f32<OT>(v[pp][c]);
+            }
+        }
+    }
+}
+
 static void pad_geometry(int h, int w, int fill, int *ph, int *pw, int *top, int *left) {
     // depth.py:2106-2119 (python float == double)
     *ph = h; *pw = w; *top = 0; *left = 0;
@@ -256,6 +408,34 @@ static int launch_depth(const WarpK &k, int depth_dtype, int out_dtype, dim3 gri
         case D2S_BF16: return launch_out<RT, __nv_bfloat16>(k, out_dtype, grid, block, st);
         default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs: depth dtype %d unsupported", depth_dtype);
     }
+}
+
+template <typename RT, typename DT, typename OT>
+static int launch_fast_t(const WarpK &k, bool half, int margin, d2s_stream_t st) {
+    const int np = half ? 8 : 4, seg = kFastThreads * np;
+    dim3 grid(ceil_div(k.w, seg), k.h);
+    size_t smem = (size_t)2 * 3 * (seg + 2 * margin) * sizeof(float);
+    const bool hwc = k.osx == 3 && k.osc == 1, chw = k.osx == 1;
+    if (!hwc && !chw) return -1;
+    if (half) { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 0>), grid, kFastThreads, smem, st, k, margin);
+                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 1>), grid, kFastThreads, smem, st, k, margin); }
+    else      { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 0>), grid, kFastThreads, smem, st, k, margin);
+                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 1>), grid, kFastThreads, smem, st, k, margin); }
+    return D2S_OK;
+}
+// Instantiated for the dtype combinations the pipeline produces; anything else (-1) takes the generic kernel.
+static int launch_fast(const WarpK &k, int rgb_dt, int depth_dt, int out_dt, bool half, int margin, d2s_stream_t st) {
+#define D2S_FAST(RD, RT, DD, DT, OD, OT) if (rgb_dt == RD && depth_dt == DD && out_dt == OD) return launch_fast_t<RT, DT, OT>(k, half, margin, st)
+    D2S_FAST(D2S_F16, __half, D2S_F16, __half, D2S_F32, float);
+    D2S_FAST(D2S_F16, __half, D2S_F16, __half, D2S_U8, uint8_t);
+    D2S_FAST(D2S_F16, __half, D2S_F16, __half, D2S_F16, __half);
+    D2S_FAST(D2S_U8, uint8_t, D2S_F16, __half, D2S_F32, float);
+    D2S_FAST(D2S_U8, uint8_t, D2S_F16, __half, D2S_U8, uint8_t);
+    D2S_FAST(D2S_U8, uint8_t, D2S_F32, float, D2S_F32, float);
+    D2S_FAST(D2S_U8, uint8_t, D2S_F32, float, D2S_U8, uint8_t);
+    D2S_FAST(D2S_F32, float, D2S_F32, float, D2S_F32, float);
+#undef D2S_FAST
+    return -1;
 }
 
 }  // namespace d2s
@@ -304,6 +484,17 @@ extern "C" int d2s_make_sbs(const d2s_warp_params *p, d2s_stream_t stream) {
     k.ystep = p->h > 1 ? 2.0f / (float)(p->h - 1) : 0.f; k.yhalf = p->h / 2;
     k.idx_l = p->idx_left; k.idx_r = p->idx_right;
 
+    // fast path: bilinear, no pad, no index taps, Full-SBS / Full-TAB / Half-SBS with even width
+    {
+        const bool half_sbs = k.half && !k.tab;
+        const double smax = fmax(fabs(0.0 - p->convergence), fabs(1.0 - p->convergence)) * fabs(p->depth_ratio) * fabs(p->ipd_uv * p->w) * 0.05;
+        const int margin = (int)ceil(smax) + 2;
+        const char *nf = getenv("D2S_WARP_GENERIC");
+        if (!(nf && nf[0] == '1') && !k.gather && !p->fill_16_9 && !k.idx_l && !k.idx_r && (!k.half || (half_sbs && k.w % 2 == 0)) && margin <= 96) {
+            int rc = launch_fast(k, p->rgb.dtype, p->depth_dtype, p->out.dtype, half_sbs, margin, stream);
+            if (rc != -1) { if (rc == D2S_OK) D2S_POST_LAUNCH(); return rc; }
+        }
+    }
     dim3 block(128, 2);
     dim3 grid(ceil_div(ceil_div(k.ow, 4), block.x), ceil_div(k.oh, block.y));
     int rc;
