@@ -15,6 +15,7 @@
 // of the last 3x3 conv.  One plan (buffers + tensor maps + CUDA graph) is built per (B, H, W) and replayed per frame.
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
 #include <memory>
@@ -35,6 +36,7 @@ struct ShapePlan {
     int B, H, W, in_dtype, out_dtype;
     std::vector<void *> allocs;
     std::vector<std::function<int(cudaStream_t)>> ops;
+    std::deque<GemmPlan> gemms;            // stable addresses: the op lambdas hold pointers into it
     std::map<std::string, Tap> taps;
     void *in_stage = nullptr, *out_stage = nullptr;
     size_t in_bytes = 0, out_bytes = 0, total_bytes = 0;
@@ -201,13 +203,21 @@ static int plan_alloc(ShapePlan *sp, T **p, size_t count) {
     return D2S_OK;
 }
 
-static int add_gemm(ShapePlan *sp, GemmPlan gp) {
-    if (gp.scratch_bytes) {   // split-K fix-up scratch: zeroed here once, every launch leaves it zeroed
-        uint8_t *s; unsigned *c;
-        TRY(plan_alloc(sp, &s, gp.scratch_bytes)); TRY(plan_alloc(sp, &c, (size_t)gp.n_counters));
-        gp.scratch = (float *)s; gp.counters = c;
-    }
-    sp->ops.push_back([gp](cudaStream_t st) { return gemm_launch(&gp, st); });
+static int add_gemm(ShapePlan *sp, const GemmPlan &gp) {
+    sp->gemms.push_back(gp);
+    const GemmPlan *p = &sp->gemms.back();
+    sp->ops.push_back([p](cudaStream_t st) { return gemm_launch(p, st); });
+    return D2S_OK;
+}
+// Split-K scratch: the kernels of one plan run one after another on one stream, so they share ONE slab area and ONE set of
+// tile counters (zeroed once here; the last CTA of every tile resets its counter), sized for the largest user.
+static int assign_scratch(ShapePlan *sp) {
+    size_t bytes = 0; int counters = 0;
+    for (auto &g : sp->gemms) { if (g.scratch_bytes > bytes) bytes = g.scratch_bytes; if (g.n_counters > counters) counters = g.n_counters; }
+    if (!bytes) return D2S_OK;
+    uint8_t *s; unsigned *c;
+    TRY(plan_alloc(sp, &s, bytes)); TRY(plan_alloc(sp, &c, (size_t)counters));
+    for (auto &g : sp->gemms) if (g.scratch_bytes) { g.scratch = (float *)s; g.counters = c; }
     return D2S_OK;
 }
 static int add_linear(ShapePlan *sp, const __half *A, int lda, const __half *Bw, int ldb, int M, int N, int K, const GemmEpi &epi) {
@@ -368,6 +378,9 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
         sp->taps["head_conv1"] = {c1, (size_t)B * h8 * w8 * Fhp, D2S_F16};
     }
     sp->taps["depth"] = {out_stage, (size_t)B * H * W, sp->out_dtype};
+    TRY(assign_scratch(sp));
+    // the buffers were zeroed on the legacy default stream; the plan may be replayed on a non-blocking stream
+    D2S_CHECK_CUDA(cudaStreamSynchronize(0));
     return D2S_OK;
 }
 

@@ -23,7 +23,7 @@ struct GemmArgs {
     int M, N, kblocks, stages;
     int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y;
     int splits, kb_per_split;   // split-K: blockIdx.z owns k-blocks [z*kb_per_split, ...)
-    float *scratch;             // fp32 [tiles][128][BN] partial sums (self-cleaning) for the fix-up path
+    float *scratch;             // fp32 [tiles][splits][128*BN] partial-sum slabs for split-K
     unsigned *counters;         // one arrival counter per output tile
     long long *trace;           // optional: clock64 stamps of CTA (0,0,0) phases (debug)
     GemmEpi epi;
@@ -207,12 +207,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         // stage the bias while the main loop runs (the epilogue warps have nothing else to do yet)
         {
             const int t = threadIdx.x - 64, n = tile_n * BN + t;
-            if (t < BN) s_bias[t] = (e.bias && n < g.N && (MODE != MODE_X32 || blockIdx.z == 0)) ? __ldg(e.bias + n) : 0.f;
+            if (t < BN) s_bias[t] = (e.bias && n < g.N) ? __ldg(e.bias + n) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        // split-K flavours: (a) MODE_X32 -> every split adds its partial to the fp32 stream (bias from split 0 only);
-        // (b) anything else -> partials meet in an fp32 scratch tile, the last-arriving CTA runs the real epilogue.
-        const bool fixup = g.splits > 1 && MODE != MODE_X32;
+        const bool fixup = g.splits > 1;   // split-K: partials meet in fp32 scratch slabs, the last-arriving CTA runs the epilogue
         const bool has_res = MODE == MODE_C16 && (e.res1 || e.res2);
         const uint4 z4 = make_uint4(0, 0, 0, 0);
         ptx::mbar_wait(tmem_full, 0);
@@ -248,33 +246,37 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                 }
             }
         } else {
-            // (b) accumulate this split's partial tile
-            float *tile = g.scratch + ((size_t)tile_m * gridDim.x + tile_n) * (size_t)(BM * BN) + (size_t)r * BN;
+            // deterministic split-K: every split stores its fp32 partial tile in its own slab (plain stores, layout
+            // [32-col chunk][4-col group][row] so a warp's 16-byte accesses are contiguous); the CTA that arrives last adds the
+            // slabs in split order — its own partial comes straight from TMEM — and runs the real epilogue.  The order of the
+            // additions does not depend on which CTA is last, so replays are bit-identical.
+            const size_t tile_id = (size_t)tile_m * gridDim.x + tile_n;
+            float4 *slab0 = (float4 *)g.scratch + tile_id * (size_t)g.splits * (BM * BN / 4) + r;   // + z * BM*BN/4 + (c*8+j) * BM
+            float4 *mine = slab0 + (size_t)blockIdx.z * (BM * BN / 4);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    atomicAdd((float4 *)(tile + c * 32 + j), make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
-                                                                         __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])));
+                for (int j = 0; j < 8; ++j)
+                    __stcg(mine + (c * 8 + j) * BM, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                                 __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
             }
             __threadfence();
             asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-            unsigned *ctr = g.counters + (size_t)tile_m * gridDim.x + tile_n;
+            unsigned *ctr = g.counters + tile_id;
             if (threadIdx.x == 64) *flag = (atomicAdd(ctr, 1u) == (unsigned)(g.splits - 1)) ? 1u : 0u;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*flag) {                                               // last CTA of this tile: full sums are in scratch
+            if (*flag) {                                               // last CTA of this tile: every slab is complete
                 __threadfence();
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int n0 = tile_n * BN + c * 32;
                     const bool live = orow >= 0 && n0 < g.N;
                     const long long off0 = orow * e.ldc + n0;
-                    float4 acc[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = __ldcg((const float4 *)(tile + c * 32 + j * 4));
+                    uint32_t raw[32];
+                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
                     uint4 r1[4] = {z4, z4, z4, z4}, r2[4] = {z4, z4, z4, z4};
                     if (has_res && live) {
 #pragma unroll
@@ -284,13 +286,31 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                                 if (e.res2) r2[j] = __ldg((const uint4 *)(e.res2 + off0 + j * 8));
                             }
                     }
+                    float acc[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) __stcg((float4 *)(tile + c * 32 + j * 4), make_float4(0.f, 0.f, 0.f, 0.f));  // leave it clean
+                    for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+                    ptx::tmem_ld_wait();
                     if (!live) continue;
+#pragma unroll 1
+                    for (int z = 0; z < g.splits; ++z) {
+                        if (z == (int)blockIdx.z) {
+#pragma unroll
+                            for (int t = 0; t < 32; ++t) acc[t] += __uint_as_float(raw[t]);
+                        } else {
+                            const float4 *sl = slab0 + (size_t)z * (BM * BN / 4) + c * 8 * BM;
+                            float4 p[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) p[j] = __ldcg(sl + j * BM);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { acc[4 * j] += p[j].x; acc[4 * j + 1] += p[j].y; acc[4 * j + 2] += p[j].z; acc[4 * j + 3] += p[j].w; }
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (n0 + j * 8 >= g.N) break;
-                        float v[8] = {acc[2 * j].x, acc[2 * j].y, acc[2 * j].z, acc[2 * j].w, acc[2 * j + 1].x, acc[2 * j + 1].y, acc[2 * j + 1].z, acc[2 * j + 1].w};
+                        float v[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) v[t] = acc[j * 8 + t];
                         epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
                     }
                 }
@@ -398,11 +418,11 @@ static int env_int(const char *name, int dflt) {
 static void finish_plan(GemmPlan *p) {
     const int base = p->grid.x * p->grid.y;
     const GemmEpi &e = p->epi;
-    const bool atomic_ok = epi_mode(e) == MODE_X32;
+    const bool x32 = epi_mode(e) == MODE_X32;
     int splits = 1;
     const int max_splits = env_int("D2S_GEMM_MAX_SPLITS", 16);
-    if (atomic_ok) {
-        splits = kNumSMs / base;                       // atomics into the fp32 stream: splitting is free
+    if (x32) {
+        splits = kNumSMs / base;                       // bias-only epilogue into the fp32 stream: cheap fix-up
         if (splits > p->kblocks / 3) splits = p->kblocks / 3;
     } else if (base * 2 <= kNumSMs && p->kblocks >= 16) {
         splits = kNumSMs / base;                       // fix-up path: only when the chain is long and the grid small
@@ -413,8 +433,8 @@ static void finish_plan(GemmPlan *p) {
     p->kb_per_split = ceil_div(p->kblocks, splits);
     p->splits = ceil_div(p->kblocks, p->kb_per_split);   // no empty split
     p->grid.z = p->splits;
-    p->scratch_bytes = (p->splits > 1 && !atomic_ok) ? (size_t)base * BM * p->BN * sizeof(float) : 0;
-    p->n_counters = (p->splits > 1 && !atomic_ok) ? base : 0;
+    p->scratch_bytes = p->splits > 1 ? (size_t)base * p->splits * BM * p->BN * sizeof(float) : 0;
+    p->n_counters = p->splits > 1 ? base : 0;
 
     const size_t stage = kABytes + (size_t)p->BN * BK * 2;
     const size_t budget = (base * p->splits > kNumSMs) ? kMaxSmem / 2 : kMaxSmem;   // two CTAs per SM only if needed
@@ -428,7 +448,7 @@ static void finish_plan(GemmPlan *p) {
     if (env_int("D2S_VERBOSE", 0))
         fprintf(stderr, "[d2s gemm] %s M=%d N=%d K=%d BN=%d grid=(%d,%d,%d) kblocks=%d kb/split=%d stages=%d smem=%zu %s\n", p->conv ? "conv" : "lin ",
                 p->M, p->N, p->K, p->BN, p->grid.x, p->grid.y, p->grid.z, p->kblocks, p->kb_per_split, stages, p->smem,
-                p->splits > 1 ? (atomic_ok ? "split:atomic" : "split:fixup") : "");
+                p->splits > 1 ? "split-K" : "");
 }
 
 static int check_epi(const GemmEpi &e, int N) {

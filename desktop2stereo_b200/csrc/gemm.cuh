@@ -43,8 +43,8 @@ struct GemmPlan {  // everything a launch needs; built once per shape, replayed 
     int H, W, Cp, TH, TW, tiles_x, tiles_y, B;
     int kblocks;
     int splits, kb_per_split;      // split-K (grid.z)
-    size_t scratch_bytes;          // fix-up path: fp32 scratch the caller must provide ZEROED (it is left zeroed)
-    int n_counters;                // ... and this many zeroed unsigned counters
+    size_t scratch_bytes;          // split-K: fp32 slab scratch the caller must provide (contents irrelevant)
+    int n_counters;                // ... and this many ZEROED unsigned counters (each launch leaves them zeroed)
     float *scratch;
     unsigned *counters;
     long long *trace;              // debug: clock64 stamps of CTA (0,0,0)

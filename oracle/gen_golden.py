@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/depth.py) on CPU.
 
 Run in the build container only (the reference tree does not travel to the GPU box):
-    python -m oracle.gen_golden [warp] [post] [pre] [model] [e2e]
+    python -m oracle.gen_golden [warp] [post] [pre] [model] [e2e] [overlay]
 Each fixture stores the seeded inputs, the parameters and the reference's outputs, plus the
 torch/transformers versions that produced them.  Test infrastructure only.
 """
@@ -250,12 +250,46 @@ def gen_e2e(_unused):
     np.savez_compressed(os.path.join(GOLDEN, "e2e.npz"), **out)
 
 
+OVERLAY_CASES = [  # (seed, H, W, dtype, [fps per call])
+    (0, 40, 64, "float32", [59.94]), (1, 130, 200, "float16", [7.0]), (2, 61, 33, "float32", [1234.5]),
+    (3, 200, 320, "float32", [float(v) for v in np.linspace(10, 130, 23)]),     # the every-10th-call cache
+    (4, 1080, 1920, "float16", [143.7]), (5, 9, 300, "float32", [float("inf")]), (6, 60, 7, "bfloat16", [99.9]),
+]
+
+
+def overlay_rgb(seed, H, W):
+    """Low-entropy frame (the fixture compresses well), regenerable from the seed."""
+    yy, xx = np.mgrid[0:H, 0:W]
+    return np.stack([(yy * (3 + seed) + xx * (5 + c) + 40 * c) % 256 for c in range(3)]).astype(np.float32)
+
+
+def gen_overlay(depth_mod):
+    """overlay_fps with a fresh cache per case; stores the top-left crop that can hold text plus a checksum that the rest
+    of the image came back untouched."""
+    out = {"versions": _versions()}
+    for (seed, H, W, dt, fps_seq) in OVERLAY_CASES:
+        rgb = torch.from_numpy(overlay_rgb(seed, H, W)).to(getattr(torch, dt))
+        depth_mod._FPS_MASK_CACHE.update(mask=None, frame=0)
+        ch, cw = min(H, 64), min(W, 420)
+        crops = []
+        for fps in fps_seq:
+            o = depth_mod.overlay_fps(rgb, fps)
+            assert o.dtype == rgb.dtype
+            rest_same = torch.equal(o[:, ch:, :], rgb[:, ch:, :]) and torch.equal(o[:, :, cw:], rgb[:, :, cw:])
+            assert rest_same
+            crops.append(o[:, :ch, :cw].float().numpy().astype(np.uint8))
+        out[f"ov{seed}"] = np.stack(crops)
+    depth_mod._FPS_MASK_CACHE.update(mask=None, frame=0)
+    np.savez_compressed(os.path.join(GOLDEN, "overlay.npz"), **out)
+    print("overlay.npz written")
+
+
 def main(argv):
     os.makedirs(GOLDEN, exist_ok=True)
-    what = set(argv) or {"warp", "post", "pre", "model", "e2e"}
+    what = set(argv) or {"warp", "post", "pre", "model", "e2e", "overlay"}
     depth_mod = load_reference("Small")
     g = globals()
-    for name in ["warp", "post", "pre", "model", "e2e"]:
+    for name in ["warp", "post", "pre", "model", "e2e", "overlay"]:
         if name in what and f"gen_{name}" in g:
             g[f"gen_{name}"](depth_mod)
 

@@ -47,10 +47,10 @@ def test_engine_vs_golden_and_oracle(cuda_device, golden_dir, case):
     assert report["hidden_last"] <= 2e-3, report
     assert report["depth_vs_oracle"] <= 5e-3, report
     assert report["depth_vs_golden"] <= 5e-3, report
-    # replay (CUDA graph): split-K partial sums meet through fp32 atomics, so two runs differ by accumulation-order noise,
-    # which can flip the fp16 rounding of an intermediate activation: max-norm agreement is one fp16 ulp-ish, mean far lower
-    again = eng(x)
-    assert _rel(again, out) <= 3e-3 and (again - out).abs().mean().item() <= 2e-4 * out.abs().max().item()
+    # replay (CUDA graph): split-K partial sums are added in split order by the last-arriving CTA, so replays are bit-identical
+    first = out.clone()
+    for _ in range(3):
+        assert torch.equal(eng(x), first)
     assert _rel(eng(x, out_dtype=torch.float16).float(), out) <= 4e-3
     eng.close()
 
