@@ -7,14 +7,7 @@
 
 using namespace d2s;
 
-// Debug launches own a throw-away scratch for split-K plans (allocated, used, synchronised, freed).
 static int launch_with_scratch(GemmPlan &p, cudaStream_t st) {
-    void *s = nullptr, *c = nullptr;
-    if (p.scratch_bytes) {
-        D2S_CHECK_CUDA(cudaMalloc(&s, p.scratch_bytes)); D2S_CHECK_CUDA(cudaMalloc(&c, p.n_counters * sizeof(unsigned)));
-        D2S_CHECK_CUDA(cudaMemsetAsync(s, 0, p.scratch_bytes, st)); D2S_CHECK_CUDA(cudaMemsetAsync(c, 0, p.n_counters * sizeof(unsigned), st));
-        p.scratch = (float *)s; p.counters = (unsigned *)c;
-    }
     long long *tr = nullptr;
     const char *tv = getenv("D2S_GEMM_TRACE");
     if (tv && tv[0] == '1') { D2S_CHECK_CUDA(cudaMalloc(&tr, 16 * sizeof(long long))); D2S_CHECK_CUDA(cudaMemsetAsync(tr, 0, 16 * sizeof(long long), st)); p.trace = tr; }
@@ -28,7 +21,6 @@ static int launch_with_scratch(GemmPlan &p, cudaStream_t st) {
                         "epilogue start %lld | epilogue end %lld | after final sync %lld | after dealloc %lld\n",
                 h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0]);
     }
-    if (s) { cudaStreamSynchronize(st); cudaFree(s); cudaFree(c); }
     return rc;
 }
 

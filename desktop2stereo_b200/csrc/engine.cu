@@ -209,17 +209,6 @@ static int add_gemm(ShapePlan *sp, const GemmPlan &gp) {
     sp->ops.push_back([p](cudaStream_t st) { return gemm_launch(p, st); });
     return D2S_OK;
 }
-// Split-K scratch: the kernels of one plan run one after another on one stream, so they share ONE slab area and ONE set of
-// tile counters (zeroed once here; the last CTA of every tile resets its counter), sized for the largest user.
-static int assign_scratch(ShapePlan *sp) {
-    size_t bytes = 0; int counters = 0;
-    for (auto &g : sp->gemms) { if (g.scratch_bytes > bytes) bytes = g.scratch_bytes; if (g.n_counters > counters) counters = g.n_counters; }
-    if (!bytes) return D2S_OK;
-    uint8_t *s; unsigned *c;
-    TRY(plan_alloc(sp, &s, bytes)); TRY(plan_alloc(sp, &c, (size_t)counters));
-    for (auto &g : sp->gemms) if (g.scratch_bytes) { g.scratch = (float *)s; g.counters = c; }
-    return D2S_OK;
-}
 static int add_linear(ShapePlan *sp, const __half *A, int lda, const __half *Bw, int ldb, int M, int N, int K, const GemmEpi &epi) {
     GemmPlan gp;
     TRY(gemm_plan_linear(&gp, A, lda, Bw, ldb, M, N, K, epi));
@@ -378,7 +367,6 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
         sp->taps["head_conv1"] = {c1, (size_t)B * h8 * w8 * Fhp, D2S_F16};
     }
     sp->taps["depth"] = {out_stage, (size_t)B * H * W, sp->out_dtype};
-    TRY(assign_scratch(sp));
     // the buffers were zeroed on the legacy default stream; the plan may be replayed on a non-blocking stream
     D2S_CHECK_CUDA(cudaStreamSynchronize(0));
     return D2S_OK;

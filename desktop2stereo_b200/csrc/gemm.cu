@@ -23,8 +23,6 @@ struct GemmArgs {
     int M, N, kblocks, stages;
     int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y;
     int splits, kb_per_split;   // split-K: blockIdx.z owns k-blocks [z*kb_per_split, ...)
-    float *scratch;             // fp32 [tiles][splits][128*BN] partial-sum slabs for split-K
-    unsigned *counters;         // one arrival counter per output tile
     long long *trace;           // optional: clock64 stamps of CTA (0,0,0) phases (debug)
     GemmEpi epi;
 };
@@ -102,7 +100,6 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     uint64_t *empty = full + stages;
     uint64_t *tmem_full = empty + stages;
     uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
-    volatile uint32_t *flag = tmem_slot + 1;   // split-K: "this CTA arrived last"
     float *s_bias = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);  // this tile's bias (BN floats), staged by the epilogue warps during the main loop
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,7 +207,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
             if (t < BN) s_bias[t] = (e.bias && n < g.N) ? __ldg(e.bias + n) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        const bool fixup = g.splits > 1;   // split-K: partials meet in fp32 scratch slabs, the last-arriving CTA runs the epilogue
+        const bool fixup = g.splits > 1;   // split-K: this CTA only parks its partial sums; see step 2 below
         const bool has_res = MODE == MODE_C16 && (e.res1 || e.res2);
         const uint4 z4 = make_uint4(0, 0, 0, 0);
         ptx::mbar_wait(tmem_full, 0);
@@ -246,13 +243,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                 }
             }
         } else {
-            // deterministic split-K: every split stores its fp32 partial tile in its own slab (plain stores, layout
-            // [32-col chunk][4-col group][row] so a warp's 16-byte accesses are contiguous); the CTA that arrives last adds the
-            // slabs in split order — its own partial comes straight from TMEM — and runs the real epilogue.  The order of the
-            // additions does not depend on which CTA is last, so replays are bit-identical.
-            const size_t tile_id = (size_t)tile_m * gridDim.x + tile_n;
-            float4 *slab0 = (float4 *)g.scratch + tile_id * (size_t)g.splits * (BM * BN / 4) + r;   // + z * BM*BN/4 + (c*8+j) * BM
-            float4 *mine = slab0 + (size_t)blockIdx.z * (BM * BN / 4);
+            // split-K, step 1: park this split's fp32 partial tile in this CTA's shared memory (the operand ring is idle now:
+            // every TMA load has landed and every MMA has retired).  Layout [8-column unit][half][row] of float4, so a warp's
+            // 16-byte accesses are contiguous both here and when a peer CTA reads them through DSMEM.
+            float4 *part = (float4 *)smem;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t raw[32];
@@ -260,70 +254,60 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    __stcg(mine + (c * 8 + j) * BM, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                                                 __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-            unsigned *ctr = g.counters + tile_id;
-            if (threadIdx.x == 64) *flag = (atomicAdd(ctr, 1u) == (unsigned)(g.splits - 1)) ? 1u : 0u;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*flag) {                                               // last CTA of this tile: every slab is complete
-                __threadfence();
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    const int n0 = tile_n * BN + c * 32;
-                    const bool live = orow >= 0 && n0 < g.N;
-                    const long long off0 = orow * e.ldc + n0;
-                    uint32_t raw[32];
-                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-                    uint4 r1[4] = {z4, z4, z4, z4}, r2[4] = {z4, z4, z4, z4};
-                    if (has_res && live) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (n0 + j * 8 < g.N) {
-                                if (e.res1) r1[j] = __ldg((const uint4 *)(e.res1 + off0 + j * 8));
-                                if (e.res2) r2[j] = __ldg((const uint4 *)(e.res2 + off0 + j * 8));
-                            }
-                    }
-                    float acc[32];
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) acc[t] = 0.f;
-                    ptx::tmem_ld_wait();
-                    if (!live) continue;
-#pragma unroll 1
-                    for (int z = 0; z < g.splits; ++z) {
-                        if (z == (int)blockIdx.z) {
-#pragma unroll
-                            for (int t = 0; t < 32; ++t) acc[t] += __uint_as_float(raw[t]);
-                        } else {
-                            const float4 *sl = slab0 + (size_t)z * (BM * BN / 4) + c * 8 * BM;
-                            float4 p[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) p[j] = __ldcg(sl + j * BM);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) { acc[4 * j] += p[j].x; acc[4 * j + 1] += p[j].y; acc[4 * j + 2] += p[j].z; acc[4 * j + 3] += p[j].w; }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (n0 + j * 8 >= g.N) break;
-                        float v[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) v[t] = acc[j * 8 + t];
-                        epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
-                    }
-                }
-                if (threadIdx.x == 64) *ctr = 0u;
+                    part[(c * 8 + j) * BM + r] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                             __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
             }
         }
-        if (MODE == MODE_HEAD && orow >= 0 && tile_n == 0 && (!fixup || *flag)) {
+        if (MODE == MODE_HEAD && orow >= 0 && tile_n == 0) {   // (never split: the plan keeps the fused head in one CTA)
             float d = (e.final_act == ACT_SIGMOID ? apply_act<ACT_SIGMOID>(head_acc + e.b3) : fmaxf(head_acc + e.b3, 0.f)) * e.max_depth;
             if (e.depth_dtype == D2S_F16) ((__half *)e.depth_out)[orow] = __float2half_rn(d);
             else ((float *)e.depth_out)[orow] = d;
         }
         if (threadIdx.x == 64) D2S_STAMP(7);
         ptx::tc_fence_before();
+    }
+    if (g.splits > 1) {
+        // split-K, step 2: the CTAs of one output tile form a thread-block cluster (cluster dims (1,1,splits)).  After the
+        // cluster barrier every partial tile is visible through distributed shared memory; CTA z reduces the 8-column units
+        // u = z, z + splits, ... by adding the partials in split order 0..splits-1 (the same order whichever CTA does it, so
+        // replays are bit-identical) and runs the fused epilogue on them.  No global scratch, no atomics on partial sums.
+        ptx::cluster_sync();
+        if (warp >= 2) {
+            const GemmEpi &e = g.epi;
+            const int r = (warp & 3) * 32 + lane;
+            long long orow;
+            if (g.conv) {
+                int y = y0 + (r >> g.TW_shift), x = x0 + (r & (g.TW - 1));
+                orow = (y < g.H && x < g.W) ? ((long long)img * g.H + y) * g.W + x : -1;
+            } else {
+                int m = tile_m * BM + r;
+                orow = m < g.M ? m : -1;
+            }
+            const bool has_res = MODE == MODE_C16 && (e.res1 || e.res2);
+            const uint32_t part0 = ptx::smem_u32(smem) + (uint32_t)r * 16u;
+            float head_acc = 0.f;
+#pragma unroll 1
+            for (int u = blockIdx.z; u < BN / 8; u += g.splits) {
+                const int n = tile_n * BN + u * 8;
+                const bool live = orow >= 0 && n < g.N;
+                const long long off = orow * e.ldc + n;
+                uint4 r1 = make_uint4(0, 0, 0, 0), r2 = r1;
+                if (has_res && live) {
+                    if (e.res1) r1 = __ldg((const uint4 *)(e.res1 + off));
+                    if (e.res2) r2 = __ldg((const uint4 *)(e.res2 + off));
+                }
+                float v[8];
+#pragma unroll 1
+                for (int z = 0; z < g.splits; ++z) {
+                    const uint32_t ra = ptx::mapa(part0 + (uint32_t)(u * 2) * (BM * 16u), (uint32_t)z);
+                    const float4 a = ptx::ld_dsmem_f4(ra), b = ptx::ld_dsmem_f4(ra + BM * 16u);
+                    if (z == 0) { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+                    else { v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w; }
+                }
+                if (live) epilogue8<ACT, MODE>(e, v, s_bias + u * 8, r1, r2, off, n, head_acc);
+            }
+        }
+        ptx::cluster_sync();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
     }
     __syncthreads();
     if (threadIdx.x == 0) D2S_STAMP(8);
@@ -420,8 +404,10 @@ static void finish_plan(GemmPlan *p) {
     const GemmEpi &e = p->epi;
     const bool x32 = epi_mode(e) == MODE_X32;
     int splits = 1;
-    const int max_splits = env_int("D2S_GEMM_MAX_SPLITS", 16);
-    if (x32) {
+    const int max_splits = min(env_int("D2S_GEMM_MAX_SPLITS", 8), 8);   // the splits of a tile form one cluster: portable maximum 8
+    if (epi_mode(e) == MODE_HEAD) {
+        splits = 1;                                    // the fused 1x1 head reduces over all N columns inside one thread
+    } else if (x32) {
         splits = kNumSMs / base;                       // bias-only epilogue into the fp32 stream: cheap fix-up
         if (splits > p->kblocks / 3) splits = p->kblocks / 3;
     } else if (base * 2 <= kNumSMs && p->kblocks >= 16) {
@@ -433,8 +419,6 @@ static void finish_plan(GemmPlan *p) {
     p->kb_per_split = ceil_div(p->kblocks, splits);
     p->splits = ceil_div(p->kblocks, p->kb_per_split);   // no empty split
     p->grid.z = p->splits;
-    p->scratch_bytes = p->splits > 1 ? (size_t)base * p->splits * BM * p->BN * sizeof(float) : 0;
-    p->n_counters = p->splits > 1 ? base : 0;
 
     const size_t stage = kABytes + (size_t)p->BN * BK * 2;
     const size_t budget = (base * p->splits > kNumSMs) ? kMaxSmem / 2 : kMaxSmem;   // two CTAs per SM only if needed
@@ -502,16 +486,21 @@ int gemm_launch(const GemmPlan *p, cudaStream_t stream) {
     a.conv = p->conv; a.H = p->H; a.W = p->W; a.Cp = p->Cp; a.TW = p->TW; a.TW_shift = p->TW == 8 ? 3 : 4;
     a.tiles_x = p->tiles_x; a.tiles_y = p->tiles_y;
     a.trace = p->trace;
-    a.splits = p->splits; a.kb_per_split = p->kb_per_split; a.scratch = p->scratch; a.counters = p->counters;
-    if (p->scratch_bytes && (!p->scratch || !p->counters)) return set_error(D2S_ERR_INVALID, "gemm: split-K plan without scratch");
+    a.splits = p->splits; a.kb_per_split = p->kb_per_split;
     a.epi = p->epi;
     const int mode = epi_mode(p->epi);
     GemmKernel fn = nullptr;
     for (int i = 0; i < kNumVariants; ++i)
         if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode) fn = kVariants[i].fn;
     if (!fn) return set_error(D2S_ERR_UNSUPPORTED, "gemm: no kernel variant for BN=%d act=%d mode=%d", p->BN, p->epi.act, mode);
-    D2S_LAUNCH(fn, p->grid, kGemmThreads, p->smem, stream, a);
-    D2S_POST_LAUNCH();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = p->grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = p->smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K: the CTAs of one output tile are one cluster
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p->splits;
+    cfg.attrs = attr; cfg.numAttrs = p->splits > 1 ? 1 : 0;
+    D2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return D2S_OK;
 }
 

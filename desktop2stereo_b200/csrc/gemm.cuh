@@ -42,11 +42,7 @@ struct GemmPlan {  // everything a launch needs; built once per shape, replayed 
     int conv;             // 0 linear, 1 implicit 3x3
     int H, W, Cp, TH, TW, tiles_x, tiles_y, B;
     int kblocks;
-    int splits, kb_per_split;      // split-K (grid.z)
-    size_t scratch_bytes;          // split-K: fp32 slab scratch the caller must provide (contents irrelevant)
-    int n_counters;                // ... and this many ZEROED unsigned counters (each launch leaves them zeroed)
-    float *scratch;
-    unsigned *counters;
+    int splits, kb_per_split;      // split-K: grid.z = cluster size; partial sums meet through distributed shared memory
     long long *trace;              // debug: clock64 stamps of CTA (0,0,0)
     GemmEpi epi;
     dim3 grid;

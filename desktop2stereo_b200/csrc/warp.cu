@@ -72,26 +72,27 @@ __device__ __forceinline__ RowCtx make_row(const WarpK &k, int y) {
 
 // depth at full-res pixel (y,x) in the value set of DT.  lowres: upsample_bilinear2d (align_corners=False),
 // restated from ATen's CUDA kernel (UpSampleBilinear2d.cu): accumulate in fp32, round to DT.
+// (noinline helpers take their parameters by value: a reference to the kernel's parameter struct would force a per-thread
+// copy of the whole struct into local memory)
 template <typename DT>
-__device__ __noinline__ float load_depth_lowres(const WarpK &k, int y, int x);
+__device__ __noinline__ float load_depth_lowres(const DT *d, int dh, int dw, float dscale_h, float dscale_w, int y, int x);
 
 template <typename DT>
 __device__ __forceinline__ float load_depth(const WarpK &k, int y, int x) {
     const DT *d = (const DT *)k.depth;
     if (!k.lowres) return to_f32<DT>(__ldg(d + (size_t)y * k.w + x));
-    return load_depth_lowres<DT>(k, y, x);
+    return load_depth_lowres<DT>(d, k.dh, k.dw, k.dscale_h, k.dscale_w, y, x);
 }
 
 template <typename DT>
-__device__ __noinline__ float load_depth_lowres(const WarpK &k, int y, int x) {
-    const DT *d = (const DT *)k.depth;
-    float h1r = fmaxf(__fmaf_rn(k.dscale_h, (float)y + 0.5f, -0.5f), 0.f);
-    float w1r = fmaxf(__fmaf_rn(k.dscale_w, (float)x + 0.5f, -0.5f), 0.f);
+__device__ __noinline__ float load_depth_lowres(const DT *d, int dh, int dw, float dscale_h, float dscale_w, int y, int x) {
+    float h1r = fmaxf(__fmaf_rn(dscale_h, (float)y + 0.5f, -0.5f), 0.f);
+    float w1r = fmaxf(__fmaf_rn(dscale_w, (float)x + 0.5f, -0.5f), 0.f);
     int h1 = (int)h1r, w1 = (int)w1r;
-    int h1p = (h1 < k.dh - 1) ? 1 : 0, w1p = (w1 < k.dw - 1) ? 1 : 0;
+    int h1p = (h1 < dh - 1) ? 1 : 0, w1p = (w1 < dw - 1) ? 1 : 0;
     float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
     float w1l = __fsub_rn(w1r, (float)w1), w0l = __fsub_rn(1.f, w1l);
-    const DT *r0 = d + (size_t)h1 * k.dw, *r1 = d + (size_t)(h1 + h1p) * k.dw;
+    const DT *r0 = d + (size_t)h1 * dw, *r1 = d + (size_t)(h1 + h1p) * dw;
     float a = to_f32<DT>(__ldg(r0 + w1)), b = to_f32<DT>(__ldg(r0 + w1 + w1p));
     float c = to_f32<DT>(__ldg(r1 + w1)), e = to_f32<DT>(__ldg(r1 + w1 + w1p));
     float top = __fmaf_rn(w0l, a, __fmul_rn(w1l, b));
@@ -250,131 +251,208 @@ __global__ void __launch_bounds__(256) warp_sbs_kernel(const WarpK k) {
 // ------------------------------------------------------------------------------------------------
 // the taps of one eye pixel straight from global memory (fast kernel: the tap left the staged window, i.e. depth outside [0,1])
 template <typename RT, typename DT>
-__device__ __noinline__ float3 taps_global(const WarpK &k, int iy0, bool two, int ix0, float nw, float ne, float sw, float se) {
-    const bool okx1 = ix0 + 1 < k.w;
+__device__ __forceinline__ float stage_value(float v, bool rgb_round) {
+    if (sizeof(RT) != 1) {
+        if (rgb_round) v = round_to<DT>(v);
+        v = fminf(fmaxf(v, 0.f), 255.f);
+    }
+    return v;
+}
+template <typename RT, typename DT>
+__device__ __noinline__ float3 taps_global(const RT *rgb, long long rsc, long long rsy, long long rsx, int w, int rgb_round, int iy0, bool two,
+                                           int ix0, float nw, float ne, float sw, float se) {
+    const bool okx1 = ix0 + 1 < w;
     float o[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        float acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0, ix0), nw, 0.f);
-        if (okx1) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0, ix0 + 1), ne, acc);
+        const RT *p0 = rgb + ch * rsc + (long long)iy0 * rsy + (long long)ix0 * rsx;
+        float acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0)), rgb_round), nw, 0.f);
+        if (okx1) acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0 + rsx)), rgb_round), ne, acc);
         if (two) {
-            acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0 + 1, ix0), sw, acc);
-            if (okx1) acc = __fmaf_rn(load_rgb<RT, DT>(k, ch, iy0 + 1, ix0 + 1), se, acc);
+            acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0 + rsy)), rgb_round), sw, acc);
+            if (okx1) acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0 + rsy + rsx)), rgb_round), se, acc);
         }
         o[ch] = acc;
     }
     return make_float3(o[0], o[1], o[2]);
 }
 
-constexpr int kFastThreads = 128;
+// ---- staging: one source row segment -> fp32 plane in shared memory (clamped / rounded exactly like load_rgb) ----
+// 16 bytes of RT -> 16/sizeof(RT) staged floats
+template <typename RT, typename DT> struct StageVec;
+template <typename DT> struct StageVec<__half, DT> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void unpack(uint4 raw, bool rgb_round, float *f) {
+        const __half2 lo = __float2half2_rn(0.f), hi = __float2half2_rn(255.f);
+        const __half2 *h = (const __half2 *)&raw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // clamp in fp16 (exact: both bounds are fp16 values; rounding to DT afterwards commutes with the clamp)
+            float2 t = __half22float2(__hmin2(__hmax2(h[j], lo), hi));
+            f[2 * j] = rgb_round ? round_to<DT>(t.x) : t.x;
+            f[2 * j + 1] = rgb_round ? round_to<DT>(t.y) : t.y;
+        }
+    }
+};
+template <typename DT> struct StageVec<uint8_t, DT> {
+    static constexpr int N = 16;
+    static __device__ __forceinline__ void unpack(uint4 raw, bool, float *f) {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[4 * j] = (float)(w[j] & 0xffu); f[4 * j + 1] = (float)((w[j] >> 8) & 0xffu);
+            f[4 * j + 2] = (float)((w[j] >> 16) & 0xffu); f[4 * j + 3] = (float)(w[j] >> 24);
+        }
+    }
+};
+template <typename DT> struct StageVec<float, DT> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void unpack(uint4 raw, bool rgb_round, float *f) {
+        const float w[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = stage_value<float, DT>(w[j], rgb_round);
+    }
+};
+template <typename DT> struct StageVec<__nv_bfloat16, DT> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void unpack(uint4 raw, bool rgb_round, float *f) {
+        const __nv_bfloat16 *h = (const __nv_bfloat16 *)&raw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = stage_value<__nv_bfloat16, DT>(__bfloat162float(h[j]), rgb_round);
+    }
+};
 
-// One warped eye pixel from the staged rows.  Same arithmetic and FMA order as eye_pixel().
+// NP consecutive depth values with one vector load (pointer aligned to NP * sizeof(DT))
+template <typename DT, int NP> struct alignas(sizeof(DT) * NP <= 16 ? sizeof(DT) * NP : 16) DepthPack { DT v[NP]; };
+
+// One warped eye pixel from the staged rows.  Same arithmetic and FMA order as eye_pixel(); the east taps are taken
+// unconditionally: when ix0 + 1 == w their weights are exactly 0 (ix == ix0 after the clip) and fma(v, 0, acc) == acc.
 template <typename RT, typename DT>
-__device__ __forceinline__ float3 eye_from_smem(const WarpK &k, const RowCtx &row, bool two, const float *s0, const float *s1, int tw,
-                                                int lo, int hi, float gx) {
+__device__ __forceinline__ float3 eye_from_smem(const WarpK &k, const RowCtx &row, bool two, const float *s0, const float *s1, int pitch,
+                                                int lo, int tw, float gx) {
     const float ix = source_index(gx, k.w);
     const int ix0 = __float2int_rz(ix);   // ix >= 0 after the clip: truncation == floor
-    const float wx0 = __fsub_rn((float)(ix0 + 1), ix), wx1 = __fsub_rn(ix, (float)ix0);
+    const float fx0 = (float)ix0;
+    const float wx0 = __fsub_rn(__fadd_rn(fx0, 1.f), ix), wx1 = __fsub_rn(ix, fx0);   // (float)(ix0 + 1) == fx0 + 1 exactly (ix0 < 2^24)
     const float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
     const float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
-    const bool okx1 = ix0 + 1 < k.w;
     const int a = ix0 - lo;
-    if (a < 0 || ix0 + (okx1 ? 1 : 0) >= hi) return taps_global<RT, DT>(k, row.iy0, two, ix0, nw, ne, sw, se);
-    const int b = okx1 ? a + 1 : a;       // when !okx1 the NE/SE taps are skipped, exactly like the bounds check of grid_sample
+    const int b = a + (ix0 + 1 < k.w ? 1 : 0);
+    if (a < 0 || b >= tw) return taps_global<RT, DT>((const RT *)k.rgb, k.rsc, k.rsy, k.rsx, k.w, k.rgb_round, row.iy0, two, ix0, nw, ne, sw, se);   // depth outside [0,1]: left the window
     float o[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        float acc = __fmaf_rn(s0[ch * tw + a], nw, 0.f);
-        if (okx1) acc = __fmaf_rn(s0[ch * tw + b], ne, acc);
+        float acc = __fmaf_rn(s0[ch * pitch + a], nw, 0.f);
+        acc = __fmaf_rn(s0[ch * pitch + b], ne, acc);
         if (two) {
-            acc = __fmaf_rn(s1[ch * tw + a], sw, acc);
-            if (okx1) acc = __fmaf_rn(s1[ch * tw + b], se, acc);
+            acc = __fmaf_rn(s1[ch * pitch + a], sw, acc);
+            acc = __fmaf_rn(s1[ch * pitch + b], se, acc);
         }
         o[ch] = acc;
     }
     return make_float3(o[0], o[1], o[2]);
 }
 
+__device__ __forceinline__ float clamp255(float v) { return fminf(fmaxf(v, 0.f), 255.f); }
+
 // OL: output layout known at compile time — 0: HWC contiguous (sx = 3, sc = 1), 1: planar CHW (sx = 1)
-template <typename RT, typename DT, typename OT, int HALF, int OL>
-__global__ void __launch_bounds__(kFastThreads) warp_sbs_fast_kernel(const WarpK k, int margin) {
+// flags: bit 0 = rgb rows may be staged with 16-byte loads, bit 1 = depth rows may be read with vector loads
+template <typename RT, typename DT, typename OT, int HALF, int OL, int THREADS>
+__global__ void __launch_bounds__(THREADS) warp_sbs_fast_kernel(const WarpK k, int margin, int flags) {
     typedef typename Vec4<OT>::type V;
-    constexpr int NP = HALF ? 8 : 4;                 // source pixels per thread
-    constexpr int SEG = kFastThreads * NP;           // source pixels per block
-    extern __shared__ float s_rgb[];                 // [rows(1|2)][3][tw]
+    constexpr int NP = HALF ? 8 : 4;                 // source pixels per thread (4 output pixels per eye)
+    constexpr int SEG = THREADS * NP;                // source pixels per block
+    extern __shared__ __align__(16) float s_rgb[];   // [rows(1|2)][3][pitch]
     const int y = blockIdx.y;
     const int seg0 = blockIdx.x * SEG;
+    const int pitch = SEG + 2 * margin;              // margin is a multiple of 8 => lo, pitch are too
     const int lo = max(seg0 - margin, 0), hi = min(seg0 + SEG + margin, k.w);   // staged source columns [lo, hi)
     const int tw = hi - lo;
     const RowCtx row = make_row(k, y);
     const bool two = row.ok1 && row.wy1 != 0.f;      // second source row contributes (block-uniform)
     const int nrows = two ? 2 : 1;
-    for (int r = 0; r < nrows; ++r)
+    {
+        typedef StageVec<RT, DT> SV;
+        const bool rr = k.rgb_round;
+        const int nv = (flags & 1) ? tw / SV::N : 0;
+        for (int r = 0; r < nrows; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float *dst = s_rgb + (r * 3 + c) * tw;
-            const RT *src = (const RT *)k.rgb + c * k.rsc + (long long)(row.iy0 + r) * k.rsy + (long long)lo * k.rsx;
-            for (int x = threadIdx.x; x < tw; x += kFastThreads) {
-                float v = to_f32<RT>(__ldg(src + (long long)x * k.rsx));
-                if (sizeof(RT) != 1) {
-                    if (k.rgb_round) v = round_to<DT>(v);
-                    v = fminf(fmaxf(v, 0.f), 255.f);
+            for (int c = 0; c < 3; ++c) {
+                float *dst = s_rgb + (r * 3 + c) * pitch;
+                const RT *src = (const RT *)k.rgb + c * k.rsc + (long long)(row.iy0 + r) * k.rsy + (long long)lo * k.rsx;
+                for (int i = threadIdx.x; i < nv; i += THREADS) {
+                    float f[SV::N];
+                    SV::unpack(__ldg((const uint4 *)src + i), rr, f);
+#pragma unroll
+                    for (int j = 0; j < SV::N; j += 4) *(float4 *)(dst + i * SV::N + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                 }
-                dst[x] = v;
+                for (int x = nv * SV::N + threadIdx.x; x < tw; x += THREADS)
+                    dst[x] = stage_value<RT, DT>(to_f32<RT>(__ldg(src + (long long)x * k.rsx)), rr);
             }
-        }
+    }
     __syncthreads();
     const int x0 = seg0 + threadIdx.x * NP;
     if (x0 >= k.w) return;
-    const float *s0 = s_rgb, *s1 = s_rgb + 3 * tw;
+    const float *s0 = s_rgb, *s1 = s_rgb + 3 * pitch;
     const int npx = min(NP, k.w - x0);               // < NP only for the last thread of a row
 
-    float3 eye[2][NP];
+    float dv[NP];
+    if ((flags & 2) && npx == NP) {
+        const DepthPack<DT, NP> pk = *(const DepthPack<DT, NP> *)((const DT *)k.depth + (size_t)y * k.w + x0);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) dv[p] = to_f32<DT>(pk.v[p]);
+    } else {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) dv[p] = load_depth<DT>(k, y, min(x0 + p, k.w - 1));   // clamped duplicates are never stored
+    }
+
+    float v[2][4][3];                                // [eye][output pixel][channel]
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const int x = min(x0 + p, k.w - 1);          // clamped duplicates are computed but never stored
+        const int x = min(x0 + p, k.w - 1);
         // shift chain, depth.py:2143-2147, :2154 (identical to eye_pixel)
-        float d = round_to<DT>(__fsub_rn(load_depth<DT>(k, y, x), k.conv));
+        float d = round_to<DT>(__fsub_rn(dv[p], k.conv));
         float inv = round_to<DT>(__fmul_rn(-d, k.ratio));
         float s = round_to<DT>(__fmul_rn(inv, k.max_px));
         s = round_to<DT>(__fmul_rn(s, k.strength));
         const float sn = round_to<DT>(__fmul_rn(s, k.two_over_wm1));
         const float xs = linspace_pm1(x, k.w, k.xstep, k.xhalf);
-        eye[0][p] = eye_from_smem<RT, DT>(k, row, two, s0, s1, tw, lo, hi, __fadd_rn(xs, sn));
-        eye[1][p] = eye_from_smem<RT, DT>(k, row, two, s0, s1, tw, lo, hi, __fsub_rn(xs, sn));
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float3 c = eye_from_smem<RT, DT>(k, row, two, s0, s1, pitch, lo, tw, e ? __fsub_rn(xs, sn) : __fadd_rn(xs, sn));
+            if (!HALF) {
+                v[e][p & 3][0] = clamp255(c.x); v[e][p & 3][1] = clamp255(c.y); v[e][p & 3][2] = clamp255(c.z);   // final clamp, depth.py:2184
+            } else if ((p & 1) == 0) {
+                v[e][p >> 1][0] = c.x; v[e][p >> 1][1] = c.y; v[e][p >> 1][2] = c.z;
+            } else {   // F.interpolate(mode="area") at an exact 2:1 ratio: (a + b) / 2, then the final clamp
+                v[e][p >> 1][0] = clamp255(__fmul_rn(__fadd_rn(v[e][p >> 1][0], c.x), 0.5f));
+                v[e][p >> 1][1] = clamp255(__fmul_rn(__fadd_rn(v[e][p >> 1][1], c.y), 0.5f));
+                v[e][p >> 1][2] = clamp255(__fmul_rn(__fadd_rn(v[e][p >> 1][2], c.z), 0.5f));
+            }
+        }
     }
-    // pack: Full modes 4 px per eye; Half-SBS: 8 source px -> 4 pair-means per eye; final clamp (depth.py:2184)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        float v[4][3];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            float3 a = HALF ? make_float3(__fmul_rn(__fadd_rn(eye[e][2 * p].x, eye[e][2 * p + 1].x), 0.5f),
-                                          __fmul_rn(__fadd_rn(eye[e][2 * p].y, eye[e][2 * p + 1].y), 0.5f),
-                                          __fmul_rn(__fadd_rn(eye[e][2 * p].z, eye[e][2 * p + 1].z), 0.5f))
-                            : eye[e][p];
-            v[p][0] = fminf(fmaxf(a.x, 0.f), 255.f); v[p][1] = fminf(fmaxf(a.y, 0.f), 255.f); v[p][2] = fminf(fmaxf(a.z, 0.f), 255.f);
-        }
         const int oy = k.tab ? e * k.h + y : y;
         const int ox = (k.tab ? 0 : e * (HALF ? k.w / 2 : k.w)) + (HALF ? x0 / 2 : x0);
         const int valid = HALF ? npx / 2 : npx;
         OT *base = (OT *)k.out + (long long)oy * k.osy + (long long)ox * (OL == 0 ? 3 : 1);
         if (valid == 4 && ((uintptr_t)base % sizeof(V)) == 0 && (OL == 0 || (k.osc * (long long)sizeof(OT)) % sizeof(V) == 0)) {
             if (OL == 0) {
-                V *dv = (V *)base;
-                dv[0] = Vec4<OT>::pack(v[0][0], v[0][1], v[0][2], v[1][0]);
-                dv[1] = Vec4<OT>::pack(v[1][1], v[1][2], v[2][0], v[2][1]);
-                dv[2] = Vec4<OT>::pack(v[2][2], v[3][0], v[3][1], v[3][2]);
+                V *dvp = (V *)base;
+                dvp[0] = Vec4<OT>::pack(v[e][0][0], v[e][0][1], v[e][0][2], v[e][1][0]);
+                dvp[1] = Vec4<OT>::pack(v[e][1][1], v[e][1][2], v[e][2][0], v[e][2][1]);
+                dvp[2] = Vec4<OT>::pack(v[e][2][2], v[e][3][0], v[e][3][1], v[e][3][2]);
             } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) *(V *)(base + c * k.osc) = Vec4<OT>::pack(v[0][c], v[1][c], v[2][c], v[3][c]);
+                for (int c = 0; c < 3; ++c) *(V *)(base + c * k.osc) = Vec4<OT>::pack(v[e][0][c], v[e][1][c], v[e][2][c], v[e][3][c]);
             }
         } else {
-#pragma unroll 1
-            for (int i = 0; i < valid * 3; ++i) {
-                int pp = i / 3, c = i - pp * 3;
-                base[OL == 0 ? i : c * k.osc + pp] = from_f32<OT>(v[pp][c]);
-            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (pp < valid) base[OL == 0 ? pp * 3 + c : c * k.osc + pp] = from_f32<OT>(v[e][pp][c]);
         }
     }
 }
@@ -412,15 +490,22 @@ static int launch_depth(const WarpK &k, int depth_dtype, int out_dtype, dim3 gri
 
 template <typename RT, typename DT, typename OT>
 static int launch_fast_t(const WarpK &k, bool half, int margin, d2s_stream_t st) {
-    const int np = half ? 8 : 4, seg = kFastThreads * np;
+    constexpr int kFull = 256, kHalf = 128;          // threads per block: 1024 source pixels per block either way
+    const int seg = 1024;
     dim3 grid(ceil_div(k.w, seg), k.h);
     size_t smem = (size_t)2 * 3 * (seg + 2 * margin) * sizeof(float);
     const bool hwc = k.osx == 3 && k.osc == 1, chw = k.osx == 1;
     if (!hwc && !chw) return -1;
-    if (half) { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 0>), grid, kFastThreads, smem, st, k, margin);
-                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 1>), grid, kFastThreads, smem, st, k, margin); }
-    else      { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 0>), grid, kFastThreads, smem, st, k, margin);
-                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 1>), grid, kFastThreads, smem, st, k, margin); }
+    int flags = 0;
+    // 16-byte staging loads: contiguous pixels, every row/plane start 16-byte aligned (lo is a multiple of 8... of 16 for u8)
+    const size_t es = sizeof(RT);
+    if (k.rsx == 1 && ((uintptr_t)k.rgb % 16) == 0 && (k.rsy * (long long)es) % 16 == 0 && (k.rsc * (long long)es) % 16 == 0 && (margin * es) % 16 == 0) flags |= 1;
+    const int np = half ? 8 : 4;
+    if (!k.lowres && k.w % np == 0 && ((uintptr_t)k.depth % 16) == 0) flags |= 2;
+    if (half) { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 0, kHalf>), grid, kHalf, smem, st, k, margin, flags);
+                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 1, kHalf>), grid, kHalf, smem, st, k, margin, flags); }
+    else      { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 0, kFull>), grid, kFull, smem, st, k, margin, flags);
+                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 1, kFull>), grid, kFull, smem, st, k, margin, flags); }
     return D2S_OK;
 }
 // Instantiated for the dtype combinations the pipeline produces; anything else (-1) takes the generic kernel.
@@ -488,9 +573,9 @@ extern "C" int d2s_make_sbs(const d2s_warp_params *p, d2s_stream_t stream) {
     {
         const bool half_sbs = k.half && !k.tab;
         const double smax = fmax(fabs(0.0 - p->convergence), fabs(1.0 - p->convergence)) * fabs(p->depth_ratio) * fabs(p->ipd_uv * p->w) * 0.05;
-        const int margin = (int)ceil(smax) + 2;
+        const int margin = ((int)ceil(smax) + 2 + 15) / 16 * 16;   // multiple of 16: staged windows start 16-byte aligned for every dtype
         const char *nf = getenv("D2S_WARP_GENERIC");
-        if (!(nf && nf[0] == '1') && !k.gather && !p->fill_16_9 && !k.idx_l && !k.idx_r && (!k.half || (half_sbs && k.w % 2 == 0)) && margin <= 96) {
+        if (!(nf && nf[0] == '1') && !k.gather && !p->fill_16_9 && !k.idx_l && !k.idx_r && (!k.half || (half_sbs && k.w % 2 == 0)) && margin <= 128) {
             int rc = launch_fast(k, p->rgb.dtype, p->depth_dtype, p->out.dtype, half_sbs, margin, stream);
             if (rc != -1) { if (rc == D2S_OK) D2S_POST_LAUNCH(); return rc; }
         }
