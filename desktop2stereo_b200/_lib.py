@@ -40,7 +40,8 @@ class ModelConfig(C.Structure):
                 ("patch", C.c_int32), ("pos_grid", C.c_int32), ("out_indices", C.c_int32 * 4),
                 ("neck", C.c_int32 * 4), ("fusion", C.c_int32), ("head_hidden", C.c_int32),
                 ("layer_norm_eps", C.c_float), ("max_depth", C.c_float), ("metric", C.c_int32),
-                ("max_batch", C.c_int32), ("max_h", C.c_int32), ("max_w", C.c_int32)]
+                ("max_batch", C.c_int32), ("max_h", C.c_int32), ("max_w", C.c_int32),
+                ("temporal", C.c_int32), ("pos_interp_offset", C.c_float), ("reserved", C.c_int32 * 2)]
 
 
 class PostParams(C.Structure):
@@ -64,6 +65,7 @@ SYMBOLS = {
     "d2s_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(ModelConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "d2s_destroy": (C.c_int, [C.c_void_p]),
     "d2s_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "d2s_reset_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "d2s_debug_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
     "d2s_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "d2s_launch_count": (C.c_int64, []),

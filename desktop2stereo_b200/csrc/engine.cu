@@ -34,6 +34,8 @@ struct Tap { const void *ptr; size_t n; int dtype; };
 
 struct ShapePlan {
     int B, H, W, in_dtype, out_dtype;
+    cudaStream_t stream = nullptr;         // the stream this plan is bound to (temporal engines keep per-stream state)
+    long long *frame_counter = nullptr;    // temporal: frames seen on this stream (device)
     std::vector<void *> allocs;
     std::vector<std::function<int(cudaStream_t)>> ops;
     std::deque<GemmPlan> gemms;            // stable addresses: the op lambdas hold pointers into it
@@ -55,6 +57,13 @@ struct LayerW {
 };
 struct RcuW { __half *c1_w, *c2_w; float *c1_b, *c2_b; };
 struct FusionW { __half *proj_w; float *proj_b; RcuW rl1, rl2; };
+struct TAttnW { float *ln_w, *ln_b, *pe, *out_b; __half *qkv_w, *out_w; };          // pe: [32, 3C] = pe @ {q,k,v}^T
+struct TemporalW {                                                                   // one TemporalModule (motion_module.py:31-134)
+    int C;
+    float *gn_w, *gn_b, *in_b, *ffln_w, *ffln_b, *ff1_b, *ff2_b, *out_b;
+    __half *in_w, *ff1_w, *ff2_w, *out_w;
+    TAttnW att[2];
+};
 
 }  // namespace d2s
 
@@ -74,6 +83,7 @@ struct d2s_engine {
     __half *neck_w[4];
     d2s::FusionW fus[4];
     __half *head_c1_w, *head_c2_w; float *head_c1_b, *head_c2_b, *head_c3_w; float head_c3_b;
+    d2s::TemporalW tm[4];                                              // cfg.temporal only
     std::map<std::vector<long long>, std::unique_ptr<d2s::ShapePlan>> plans;   // keyed by shape, dtypes AND stream
     std::mutex mu;
     d2s::ShapePlan *last = nullptr;
@@ -179,8 +189,29 @@ static int upload_weights(d2s_engine *e, const void *blob, size_t nbytes) {
         TRY(load_f32(e, r, &e->head_c3_w, c.head_hidden, st));
         return D2S_OK;
     }();
+    const float *b3 = rc == D2S_OK ? r.take(1) : nullptr;
+    if (rc == D2S_OK && c.temporal) rc = [&]() -> int {
+        const int Cs[4] = {e->c[2], e->c[3], F, F};
+        for (int m = 0; m < 4; ++m) {
+            TemporalW &t = e->tm[m];
+            const int C = t.C = Cs[m];
+            TRY(load_f32(e, r, &t.gn_w, C, st)); TRY(load_f32(e, r, &t.gn_b, C, st));
+            TRY(load_mat(e, r, &t.in_w, C, C, C, st)); TRY(load_f32(e, r, &t.in_b, C, st));
+            for (int a = 0; a < 2; ++a) {
+                TAttnW &w = t.att[a];
+                TRY(load_f32(e, r, &w.ln_w, C, st)); TRY(load_f32(e, r, &w.ln_b, C, st));
+                TRY(load_mat(e, r, &w.qkv_w, 3 * C, C, C, st));
+                TRY(load_f32(e, r, &w.pe, (size_t)32 * 3 * C, st));
+                TRY(load_mat(e, r, &w.out_w, C, C, C, st)); TRY(load_f32(e, r, &w.out_b, C, st));
+            }
+            TRY(load_f32(e, r, &t.ffln_w, C, st)); TRY(load_f32(e, r, &t.ffln_b, C, st));
+            TRY(load_mat(e, r, &t.ff1_w, 8 * C, C, C, st)); TRY(load_f32(e, r, &t.ff1_b, 8 * C, st));
+            TRY(load_mat(e, r, &t.ff2_w, C, 4 * C, 4 * C, st)); TRY(load_f32(e, r, &t.ff2_b, C, st));
+            TRY(load_mat(e, r, &t.out_w, C, C, C, st)); TRY(load_f32(e, r, &t.out_b, C, st));
+        }
+        return D2S_OK;
+    }();
     if (rc == D2S_OK) {
-        const float *b3 = r.take(1);
         if (!r.ok || r.off != r.n) rc = set_error(D2S_ERR_INVALID, "d2s_create: weight blob has %zu floats, the config needs %zu", r.n, r.off);
         else if (cudaMemcpy(&e->head_c3_b, b3, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(D2S_ERR_CUDA, "d2s_create: blob readback failed");
     }
@@ -232,6 +263,48 @@ static int add_rcu(ShapePlan *sp, const RcuW &w, const __half *x, const __half *
     return D2S_OK;
 }
 
+// One TemporalModule on an NHWC fp16 map x [d, Cp] of one frame -> out [d, Cp] (motion_module.py:103-134; streaming form, see
+// temporal.cu).  Kernels: GroupNorm (2) | proj_in GEMM | 2 x (LN, qkv GEMM, ring attention, out GEMM) | LN, ff1 GEMM, GEGLU,
+// ff2 GEMM | cast, proj_out GEMM (+ residual x) = 18 launches, all GEMMs on the tcgen05 kernel.
+static int add_temporal(ShapePlan *sp, const TemporalW &t, const __half *x, __half *out, int d, int Cp, int m) {
+    const int C = t.C;
+    float *part, *hs;
+    __half *gn16, *ln16, *qkv16, *att16, *ff16, *gg16, *hs16;
+    TRY(plan_alloc(sp, &part, groupnorm32_partial_floats(d)));
+    TRY(plan_alloc(sp, &hs, (size_t)d * C));
+    TRY(plan_alloc(sp, &gn16, (size_t)d * C)); TRY(plan_alloc(sp, &ln16, (size_t)d * C)); TRY(plan_alloc(sp, &qkv16, (size_t)d * 3 * C));
+    TRY(plan_alloc(sp, &att16, (size_t)d * C)); TRY(plan_alloc(sp, &ff16, (size_t)d * 8 * C)); TRY(plan_alloc(sp, &gg16, (size_t)d * 4 * C));
+    TRY(plan_alloc(sp, &hs16, (size_t)d * C));
+    const float *gw = t.gn_w, *gb = t.gn_b;
+    sp->ops.push_back([=](cudaStream_t st) { return groupnorm32_launch(x, part, gw, gb, gn16, d, C, Cp, 1e-6f, st); });
+    GemmEpi ei; ei.bias = t.in_b; ei.x32 = hs; ei.x32_assign = 1; ei.ldc = C;
+    TRY(add_linear(sp, gn16, C, t.in_w, C, d, C, C, ei));
+    const long long *tc = sp->frame_counter;
+    for (int a = 0; a < 2; ++a) {
+        const TAttnW w = t.att[a];
+        __half *ring;
+        TRY(plan_alloc(sp, &ring, (size_t)d * 32 * 2 * C));
+        sp->ops.push_back([=](cudaStream_t st) { return layernorm_launch(hs, w.ln_w, w.ln_b, ln16, d, C, 1e-5f, 0, 0, st); });
+        GemmEpi eq; eq.c16 = qkv16; eq.ldc = 3 * C;
+        TRY(add_linear(sp, ln16, C, w.qkv_w, C, d, 3 * C, C, eq));
+        sp->ops.push_back([=](cudaStream_t st) { return temporal_attention_launch(qkv16, ring, w.pe, tc, att16, d, C, st); });
+        GemmEpi eo; eo.bias = w.out_b; eo.x32 = hs; eo.ldc = C;
+        TRY(add_linear(sp, att16, C, w.out_w, C, d, C, C, eo));
+    }
+    const float *fw = t.ffln_w, *fb = t.ffln_b;
+    sp->ops.push_back([=](cudaStream_t st) { return layernorm_launch(hs, fw, fb, ln16, d, C, 1e-5f, 0, 0, st); });
+    GemmEpi e1; e1.bias = t.ff1_b; e1.c16 = ff16; e1.ldc = 8 * C;
+    TRY(add_linear(sp, ln16, C, t.ff1_w, C, d, 8 * C, C, e1));
+    sp->ops.push_back([=](cudaStream_t st) { return geglu_launch(ff16, gg16, d, 4 * C, st); });
+    GemmEpi e2; e2.bias = t.ff2_b; e2.x32 = hs; e2.ldc = C;
+    TRY(add_linear(sp, gg16, 4 * C, t.ff2_w, 4 * C, d, C, 4 * C, e2));
+    sp->ops.push_back([=](cudaStream_t st) { return cast_f16_launch(hs, hs16, (long long)d * C, st); });
+    GemmEpi eo; eo.bias = t.out_b; eo.res1 = x; eo.c16 = out; eo.ldc = Cp;
+    TRY(add_linear(sp, hs16, C, t.out_w, C, d, C, C, eo));
+    sp->taps["temporal" + std::to_string(m)] = {out, (size_t)d * Cp, D2S_F16};
+    return D2S_OK;
+}
+
 static int build_plan(d2s_engine *e, ShapePlan *sp) {
     const d2s_model_config &c = e->cfg;
     const int B = sp->B, H = sp->H, W = sp->W, D = e->D, F = e->F;
@@ -241,6 +314,7 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     sp->out_bytes = (size_t)B * H * W * out_es;
     uint8_t *in_stage, *out_stage;
     TRY(plan_alloc(sp, &in_stage, sp->in_bytes)); TRY(plan_alloc(sp, &out_stage, sp->out_bytes));
+    if (c.temporal) TRY(plan_alloc(sp, &sp->frame_counter, 1));
     sp->in_stage = in_stage; sp->out_stage = out_stage;
 
     // ---------------- embeddings ----------------
@@ -251,7 +325,10 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     TRY(plan_alloc(sp, &pos, (size_t)N * D));
     // position table for this grid: input independent, computed once here (HF dinov2:57-96)
     if (ph == c.pos_grid && pw == c.pos_grid) D2S_CHECK_CUDA(cudaMemcpy(pos, e->pos_table, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToDevice));
-    else TRY(pos_embed_interp_launch(e->pos_table, pos, c.pos_grid, ph, pw, D, 0));
+    else if (c.pos_interp_offset != 0.f)   // VDA: F.interpolate(scale_factor=((ph+off)/g, (pw+off)/g)) -> source step = 1/scale_factor (dinov2.py:190-203)
+        TRY(pos_embed_interp_launch(e->pos_table, pos, c.pos_grid, ph, pw, D, (float)(1.0 / ((double)(float)(ph + c.pos_interp_offset) / (double)c.pos_grid)),
+                                    (float)(1.0 / ((double)(float)(pw + c.pos_interp_offset) / (double)c.pos_grid)), 0));
+    else TRY(pos_embed_interp_launch(e->pos_table, pos, c.pos_grid, ph, pw, D, (float)c.pos_grid / (float)ph, (float)c.pos_grid / (float)pw, 0));
     D2S_CHECK_CUDA(cudaStreamSynchronize(0));
     {
         const int in_dtype = sp->in_dtype, patch = c.patch, Kp = e->Kpatch;
@@ -322,6 +399,14 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
         TRY(add_linear(sp, col3, 9 * cp3, e->dn3_w, 9 * cp3, B * h3 * w3, e->c[3], 9 * cp3, ed));
     }
     for (int i = 0; i < 4; ++i) sp->taps["reassemble" + std::to_string(i)] = {R[i], (size_t)B * hs[i] * ws[i] * e->cp[i], D2S_F16};
+    if (c.temporal) {   // dpt_temporal.py:92-95: temporal modules on layer_3 and layer_4 before the neck convs
+        for (int i = 2; i < 4; ++i) {
+            __half *o;
+            TRY(plan_alloc(sp, &o, (size_t)hs[i] * ws[i] * e->cp[i]));
+            TRY(add_temporal(sp, e->tm[i - 2], R[i], o, hs[i] * ws[i], e->cp[i], i - 2));
+            R[i] = o;
+        }
+    }
 
     // ---------------- neck convs (3x3, no bias) -> features + relu copies ----------------
     __half *Fm[4], *Fr[4];
@@ -351,6 +436,12 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
         TRY(add_linear(sp, up, F, e->fus[j].proj_w, F, B * oh * ow, F, F, ep));
         hidden = proj;
         sp->taps["fused" + std::to_string(j)] = {proj, no, D2S_F16};
+        if (c.temporal && j < 2) {   // dpt_temporal.py:102-107: temporal modules on path_4 and path_3
+            __half *o;
+            TRY(plan_alloc(sp, &o, no));
+            TRY(add_temporal(sp, e->tm[2 + j], proj, o, oh * ow, F, 2 + j));
+            hidden = o;
+        }
     }
 
     // ---------------- head (HF depth_anything:292-308) ----------------
@@ -367,6 +458,7 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
         sp->taps["head_conv1"] = {c1, (size_t)B * h8 * w8 * Fhp, D2S_F16};
     }
     sp->taps["depth"] = {out_stage, (size_t)B * H * W, sp->out_dtype};
+    if (c.temporal) { long long *fc = sp->frame_counter; sp->ops.push_back([=](cudaStream_t st) { return frame_counter_inc_launch(fc, st); }); }
     // the buffers were zeroed on the legacy default stream; the plan may be replayed on a non-blocking stream
     D2S_CHECK_CUDA(cudaStreamSynchronize(0));
     return D2S_OK;
@@ -394,6 +486,8 @@ extern "C" int d2s_create(const void *weight_blob, size_t nbytes, const d2s_mode
     D2S_REQUIRE(cfg->patch == 14 && cfg->head_hidden == 32, "d2s_create: patch must be 14 and head_hidden 32");
     D2S_REQUIRE(cfg->fusion % 64 == 0 && cfg->mlp_hidden % 64 == 0, "d2s_create: fusion/mlp sizes must be multiples of 64");
     for (int i = 0; i < 4; ++i) D2S_REQUIRE(cfg->neck[i] % 8 == 0 && cfg->neck[i] > 0, "d2s_create: neck[%d]=%d must be a positive multiple of 8", i, cfg->neck[i]);
+    if (cfg->temporal)
+        D2S_REQUIRE(cfg->neck[2] % 64 == 0 && cfg->neck[3] % 64 == 0 && cfg->fusion % 64 == 0, "d2s_create: temporal modules need neck[2], neck[3] and fusion to be multiples of 64");
     D2S_CHECK_CUDA(cudaSetDevice(device));
     int rc = gemm_init();
     if (rc) return rc;
@@ -426,6 +520,7 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
     D2S_REQUIRE(B >= 1 && H >= 14 && W >= 14 && H % h->cfg.patch == 0 && W % h->cfg.patch == 0, "d2s_infer: input %dx%dx%d must be a multiple of the patch size", B, H, W);
     D2S_REQUIRE(in_dtype == D2S_F32 || in_dtype == D2S_F16, "d2s_infer: pixel_values dtype %d", in_dtype);
     D2S_REQUIRE(out_dtype == D2S_F32 || out_dtype == D2S_F16, "d2s_infer: output dtype %d", out_dtype);
+    D2S_REQUIRE(!h->cfg.temporal || B == 1, "d2s_infer: a temporal (Video-Depth-Anything) engine takes one frame per call (B=%d)", B);
     cudaStream_t st = (cudaStream_t)stream;
     // One plan (activation buffers + tensor maps + graph) per shape AND per stream: frames submitted on different streams
     // run concurrently on disjoint buffers while sharing the (read-only) weights.
@@ -436,7 +531,7 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
         // first frame of this shape: allocate buffers, encode tensor maps, capture the graph (the only host-synchronous path,
         // like the reference's lazy engine build at depth.py:1842-1862)
         std::unique_ptr<ShapePlan> sp(new ShapePlan());
-        sp->B = B; sp->H = H; sp->W = W; sp->in_dtype = in_dtype; sp->out_dtype = out_dtype;
+        sp->B = B; sp->H = H; sp->W = W; sp->in_dtype = in_dtype; sp->out_dtype = out_dtype; sp->stream = st;
         int rc = build_plan(h, sp.get());
         if (rc) return rc;
         if (h->use_graph) {
@@ -463,6 +558,15 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
         if (rc) return rc;
     }
     D2S_CHECK_CUDA(cudaMemcpyAsync(depth_out, sp->out_stage, sp->out_bytes, cudaMemcpyDeviceToDevice, st));
+    return D2S_OK;
+}
+
+extern "C" int d2s_reset_stream(d2s_handle h, d2s_stream_t stream) {
+    D2S_REQUIRE(h != nullptr, "d2s_reset_stream: null handle");
+    std::unique_lock<std::mutex> lock(h->mu);
+    for (auto &kv : h->plans)
+        if (kv.second->stream == (cudaStream_t)stream && kv.second->frame_counter)
+            D2S_CHECK_CUDA(cudaMemsetAsync(kv.second->frame_counter, 0, sizeof(long long), (cudaStream_t)stream));
     return D2S_OK;
 }
 

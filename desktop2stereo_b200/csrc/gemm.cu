@@ -64,8 +64,13 @@ __device__ __forceinline__ void epilogue8(const GemmEpi &e, float (&v)[8], const
     } else if (MODE == MODE_X32) {
         // fire-and-forget reductions into the fp32 stream (no load round trip; one add per element and GEMM when splits == 1)
         float4 *p = (float4 *)(e.x32 + off);
-        atomicAdd(p, make_float4(v[0], v[1], v[2], v[3]));
-        atomicAdd(p + 1, make_float4(v[4], v[5], v[6], v[7]));
+        if (e.x32_assign) {
+            p[0] = make_float4(v[0], v[1], v[2], v[3]);
+            p[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            atomicAdd(p, make_float4(v[0], v[1], v[2], v[3]));
+            atomicAdd(p + 1, make_float4(v[4], v[5], v[6], v[7]));
+        }
     } else {
         if (e.res1) {
             const __half2 *h = (const __half2 *)&r1;

@@ -18,7 +18,8 @@ struct GemmEpi {
     const __half *res2 = nullptr;
     __half *c16 = nullptr;           // fp16 output
     __half *c16_relu = nullptr;      // optional relu(v) copy (input of the next pre-activation conv)
-    float *x32 = nullptr;            // fp32 residual stream: x32[row, col] += v
+    float *x32 = nullptr;            // fp32 residual stream: x32[row, col] += v   (x32_assign: = v)
+    int x32_assign = 0;
     float *c32 = nullptr;            // fp32 output (plain store)
     int ldc = 0;                     // leading dimension (elements) of every output / residual above
     // fused 1x1 head (requires N <= 32): depth[row] = final_act(sum_n v[n] * w3[n] + b3) * max_depth

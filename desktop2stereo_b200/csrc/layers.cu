@@ -13,19 +13,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
     long long in_row = row;
     if (skip_cls) { int P = tokens_per_img - 1; in_row = (long long)(row / P) * tokens_per_img + 1 + row % P; }
     const float4 *xr = (const float4 *)(x + in_row * D);
-    const int nv = D >> 7;  // float4 per lane (D multiple of 128)
+    const int nv = (D + 127) >> 7;  // float4 slots per lane; slot i of a lane covers channels (lane + 32 i) * 4 .. + 3 when < D
     float4 v[8];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        if (i < nv) { v[i] = xr[lane + i * 32]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+        if (i < nv && (lane + i * 32) * 4 < D) { v[i] = xr[lane + i * 32]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / (float)D;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        if (i < nv) {
+        if (i < nv && (lane + i * 32) * 4 < D) {
             float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
             sq += a * a + b * b + c * c + d * d;
         }
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
     __half *yr = y + (long long)row * D;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        if (i < nv) {
+        if (i < nv && (lane + i * 32) * 4 < D) {
             int c = (lane + i * 32) * 4;
             float4 g = __ldg((const float4 *)(gamma + c)), b = __ldg((const float4 *)(beta + c));
             __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 
 int layernorm_launch(const float *x, const float *gamma, const float *beta, __half *y, int rows, int D, float eps,
                      int skip_cls, int tokens_per_img, cudaStream_t stream) {
-    D2S_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
+    D2S_REQUIRE(D % 4 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 4 and <= 1024", D);
     D2S_LAUNCH(layernorm_kernel, ceil_div(rows, 8), 256, 0, stream, x, gamma, beta, y, rows, D, eps, skip_cls, tokens_per_img);
     D2S_POST_LAUNCH();
     return D2S_OK;
@@ -102,7 +102,7 @@ int assemble_tokens_launch(const __half *patches, const float *cls, const float 
 __device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
 __device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
 
-__global__ void pos_embed_interp_kernel(const float *__restrict__ table, float *__restrict__ out, int g, int ph, int pw, int D) {
+__global__ void pos_embed_interp_kernel(const float *__restrict__ table, float *__restrict__ out, int g, int ph, int pw, int D, float sy, float sx) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)(1 + ph * pw) * D;
     if (i >= total) return;
@@ -111,7 +111,6 @@ __global__ void pos_embed_interp_kernel(const float *__restrict__ table, float *
     if (tok == 0) { out[i] = table[d]; return; }   // class position embedding is kept as is
     int py = (tok - 1) / pw, px = (tok - 1) % pw;
     const float A = -0.75f;
-    float sy = (float)g / (float)ph, sx = (float)g / (float)pw;
     float ry = sy * ((float)py + 0.5f) - 0.5f, rx = sx * ((float)px + 0.5f) - 0.5f;
     int iy = (int)floorf(ry), ix = (int)floorf(rx);
     float ty = ry - (float)iy, tx = rx - (float)ix;
@@ -132,9 +131,9 @@ __global__ void pos_embed_interp_kernel(const float *__restrict__ table, float *
     out[i] = acc;
 }
 
-int pos_embed_interp_launch(const float *pos_table, float *pos_out, int grid, int ph, int pw, int D, cudaStream_t stream) {
+int pos_embed_interp_launch(const float *pos_table, float *pos_out, int grid, int ph, int pw, int D, float scale_y, float scale_x, cudaStream_t stream) {
     long long total = (long long)(1 + ph * pw) * D;
-    D2S_LAUNCH(pos_embed_interp_kernel, ceil_div(total, 256), 256, 0, stream, pos_table, pos_out, grid, ph, pw, D);
+    D2S_LAUNCH(pos_embed_interp_kernel, ceil_div(total, 256), 256, 0, stream, pos_table, pos_out, grid, ph, pw, D, scale_y, scale_x);
     D2S_POST_LAUNCH();
     return D2S_OK;
 }

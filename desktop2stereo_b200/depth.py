@@ -106,7 +106,7 @@ def predict_depth(image_rgb, return_tuple=False, use_temporal_smooth: bool = Tru
     x = preprocess(src, settings.depth_resolution, settings.patch, dtype=torch.float32, layout=layout,
                    mean=IMAGENET_MEAN, std=IMAGENET_STD)
     raw = model_wraper(x)                                  # [1,H',W'] fp16
-    depth = depth_stabilizer(raw[0], out_size=(h, w), use_temporal_smooth=use_temporal_smooth)
+    depth = depth_stabilizer(raw.reshape(raw.shape[-2:]), out_size=(h, w), use_temporal_smooth=use_temporal_smooth)
     if return_tuple:
         return depth, rgb_tensor
     return depth

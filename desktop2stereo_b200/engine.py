@@ -39,6 +39,14 @@ class B200Engine:
         return cls(pack_state_dict(model.state_dict(), cfg), cfg, device, out_dtype)
 
     @classmethod
+    def from_vda_state_dict(cls, state_dict, encoder: str, device=None, out_dtype=torch.float16):
+        """state_dict of the reference's VideoDepthAnything (vda2_s.py; depth.py:870-902), encoder in vits/vitb/vitl.
+        The engine is then a streaming one: one frame per call, state per CUDA stream, `reset()` starts a new video."""
+        from .weights import config_for_vda, pack_vda_state_dict
+        cfg = config_for_vda(encoder)
+        return cls(pack_vda_state_dict(state_dict, cfg), cfg, device, out_dtype)
+
+    @classmethod
     def from_state_dict(cls, state_dict, hf_config, device=None, out_dtype=torch.float16):
         cfg = config_from_hf(hf_config)
         return cls(pack_state_dict(state_dict, cfg), cfg, device, out_dtype)
@@ -59,7 +67,12 @@ class B200Engine:
         with torch.cuda.device(tensor.device):
             _lib.check(_lib.lib().d2s_infer(self._h, tensor.data_ptr(), _TORCH2D2S[tensor.dtype], out.data_ptr(),
                                             _TORCH2D2S[odt], B, H, W, _stream_ptr(tensor.device)), "d2s_infer")
-        return out
+        return out.view(B, 1, H, W) if self.cfg.temporal else out     # VDA returns [T,1,H,W] (vda2_s.py:80-84)
+
+    def reset(self):
+        """Temporal engines: forget the state of the current stream (the next frame is a first frame, vda2_s.py:196)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().d2s_reset_stream(self._h, _stream_ptr(self.device)), "d2s_reset_stream")
 
     def tap(self, name: str) -> torch.Tensor:
         """Debug/parity tap: an internal activation of the last inference, as a flat fp32 tensor."""

@@ -11,7 +11,12 @@ Blob order (all fp32, row-major, nn.Module layouts unless noted):
     fusion layers j=0..3: proj_w [F,F] proj_b | rl1.conv1 w b | rl1.conv2 w b | rl2.conv1 w b | rl2.conv2 w b
     head: conv1 w [F/2,F,3,3] b | conv2 w [32,F/2,3,3] b | conv3 w [32] b [1]
 
-Reference loading path this stands in for: depth.py:1633-1690 (_load_pytorch_model) + HF from_pretrained.
+    temporal engines (Video-Depth-Anything) append, for each of the 4 TemporalModules (C = c2, c3, F, F):
+        gn_w gn_b | proj_in_w [C,C] b | 2 x (ln_w ln_b | qkv_w [3C,C] (to_q;to_k;to_v, bias-free) | pe_qkv [32,3C] = pe @ qkv_w^T |
+        out_w [C,C] out_b) | ffln_w ffln_b | ff1_w [8C,C] b | ff2_w [C,4C] b | proj_out_w [C,C] b
+
+Reference loading path this stands in for: depth.py:1633-1690 (_load_pytorch_model) + HF from_pretrained, and
+depth.py:870-902 (get_video_depth_anything_model: torch.load of video_depth_anything_{vits,vitb,vitl}.pth).
 """
 from __future__ import annotations
 
@@ -87,4 +92,77 @@ def pack_state_dict(sd: dict, cfg: ModelConfig) -> np.ndarray:
                     g(f + rl + "convolution2.weight"), g(f + rl + "convolution2.bias")]
     out += [g("head.conv1.weight"), g("head.conv1.bias"), g("head.conv2.weight"), g("head.conv2.bias"),
             g("head.conv3.weight").reshape(-1), g("head.conv3.bias").reshape(1)]
+    return np.concatenate([a.reshape(-1) for a in out]).astype(np.float32, copy=False)
+
+
+# Video-Depth-Anything encoders (depth.py:889-893; dinov2.py:339-377; vda2_s.py:52-56)
+VDA_ENCODERS = {
+    "vits": dict(hidden=384, layers=12, heads=6, taps=[2, 5, 8, 11], features=64, out_channels=[48, 96, 192, 384]),
+    "vitb": dict(hidden=768, layers=12, heads=12, taps=[2, 5, 8, 11], features=128, out_channels=[96, 192, 384, 768]),
+    "vitl": dict(hidden=1024, layers=24, heads=16, taps=[4, 11, 17, 23], features=256, out_channels=[256, 512, 1024, 1024]),
+}
+
+
+def config_for_vda(encoder: str, max_h=518, max_w=518) -> ModelConfig:
+    e = VDA_ENCODERS[encoder]
+    c = ModelConfig()
+    c.hidden, c.layers, c.heads, c.mlp_hidden = e["hidden"], e["layers"], e["heads"], 4 * e["hidden"]
+    c.patch, c.pos_grid = 14, 37
+    for i in range(4):
+        c.out_indices[i] = e["taps"][i] + 1          # block index (0-based) -> hidden-state index (1-based)
+        c.neck[i] = e["out_channels"][i]
+    c.fusion, c.head_hidden = e["features"], 32
+    c.layer_norm_eps, c.metric, c.max_depth = 1e-6, 0, 1.0
+    c.max_batch, c.max_h, c.max_w = 1, max_h, max_w
+    c.temporal, c.pos_interp_offset = 1, 0.1
+    return c
+
+
+def pack_vda_state_dict(sd: dict, cfg: ModelConfig) -> np.ndarray:
+    """sd: state_dict of the reference's VideoDepthAnything (vda2_s.py) -> the fp32 blob of a temporal engine."""
+
+    def g(name):
+        t = sd[name]
+        if hasattr(t, "detach"):
+            t = t.detach().to("cpu").float().numpy()
+        return np.ascontiguousarray(t, dtype=np.float32)
+
+    D, L, F = cfg.hidden, cfg.layers, cfg.fusion
+    out = [g("pretrained.patch_embed.proj.weight").reshape(D, -1), g("pretrained.patch_embed.proj.bias"),
+           g("pretrained.cls_token").reshape(D), g("pretrained.pos_embed").reshape(-1, D)]
+    for l in range(L):
+        p = f"pretrained.blocks.{l}."
+        ls1, ls2 = g(p + "ls1.gamma"), g(p + "ls2.gamma")
+        out += [g(p + "norm1.weight"), g(p + "norm1.bias"), g(p + "attn.qkv.weight"), g(p + "attn.qkv.bias"),
+                g(p + "attn.proj.weight") * ls1[:, None], g(p + "attn.proj.bias") * ls1,
+                g(p + "norm2.weight"), g(p + "norm2.bias"), g(p + "mlp.fc1.weight"), g(p + "mlp.fc1.bias"),
+                g(p + "mlp.fc2.weight") * ls2[:, None], g(p + "mlp.fc2.bias") * ls2]
+    out += [g("pretrained.norm.weight"), g("pretrained.norm.bias")]
+    for i in range(4):
+        out += [g(f"head.projects.{i}.weight").reshape(cfg.neck[i], D), g(f"head.projects.{i}.bias")]
+    for i in (0, 1, 3):
+        out += [g(f"head.resize_layers.{i}.weight"), g(f"head.resize_layers.{i}.bias")]
+    for i in range(4):
+        out.append(g(f"head.scratch.layer{i + 1}_rn.weight"))
+    for j in range(4):                                   # fusion order coarse -> fine: refinenet4 .. refinenet1
+        f = f"head.scratch.refinenet{4 - j}."
+        out += [g(f + "out_conv.weight").reshape(F, F), g(f + "out_conv.bias")]
+        for u in ("resConfUnit1.", "resConfUnit2."):
+            out += [g(f + u + "conv1.weight"), g(f + u + "conv1.bias"), g(f + u + "conv2.weight"), g(f + u + "conv2.bias")]
+    out += [g("head.scratch.output_conv1.weight"), g("head.scratch.output_conv1.bias"),
+            g("head.scratch.output_conv2.0.weight"), g("head.scratch.output_conv2.0.bias"),
+            g("head.scratch.output_conv2.2.weight").reshape(-1), g("head.scratch.output_conv2.2.bias").reshape(1)]
+    for m in range(4):
+        t = f"head.motion_modules.{m}.temporal_transformer."
+        b = t + "transformer_blocks.0."
+        out += [g(t + "norm.weight"), g(t + "norm.bias"), g(t + "proj_in.weight"), g(t + "proj_in.bias")]
+        for a in range(2):
+            ab = b + f"attention_blocks.{a}."
+            qkv = np.concatenate([g(ab + "to_q.weight"), g(ab + "to_k.weight"), g(ab + "to_v.weight")], 0)
+            pe = g(ab + "pos_encoder.pe")[0].astype(np.float64)             # [32, C] sinusoid (motion_module.py:190-204)
+            out += [g(b + f"norms.{a}.weight"), g(b + f"norms.{a}.bias"), qkv,
+                    (pe @ qkv.astype(np.float64).T).astype(np.float32),      # position terms of q/k/v: the projections are linear
+                    g(ab + "to_out.0.weight"), g(ab + "to_out.0.bias")]
+        out += [g(b + "ff_norm.weight"), g(b + "ff_norm.bias"), g(b + "ff.net.0.proj.weight"), g(b + "ff.net.0.proj.bias"),
+                g(b + "ff.net.2.weight"), g(b + "ff.net.2.bias"), g(t + "proj_out.weight"), g(t + "proj_out.bias")]
     return np.concatenate([a.reshape(-1) for a in out]).astype(np.float32, copy=False)

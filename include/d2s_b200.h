@@ -116,6 +116,11 @@ typedef struct d2s_model_config {
     int32_t metric;      /* 0: final ReLU, 1: final sigmoid*max_depth */
     int32_t max_batch;   /* workspace is sized for this many frames per call */
     int32_t max_h, max_w;/* largest model input (multiples of patch) */
+    /* Video-Depth-Anything (reference models/video_depth_anything/, depth.py:870-902): */
+    int32_t temporal;    /* 0: Depth Anything V2 (per-frame).  1: streaming VDA: 4 temporal modules in the DPT head, one frame per
+                            d2s_infer call (B must be 1), per-stream state = rings of the last 32 frames' K/V (vda2_s.py:177-224) */
+    float pos_interp_offset; /* 0: HF size-based pos-embed interpolation; 0.1: VDA's scale_factor form (dinov2.py:179-210) */
+    int32_t reserved[2];
 } d2s_model_config;
 
 /* weight_blob: host pointer to the packed fp32 parameter blob produced by
@@ -125,6 +130,9 @@ int d2s_destroy(d2s_handle h);
 /* pixel_values [B,3,H,W] (F16 or F32, normalised) -> predicted_depth [B,H,W] (F16 or F32). */
 int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, void *depth_out, int out_dtype,
               int B, int H, int W, d2s_stream_t stream);
+/* temporal engines: forget the stream state (frame counter + K/V rings) of the plan(s) bound to `stream` — the next frame is a
+ * first frame again (vda2_s.py:196 `if not self.transform`). */
+int d2s_reset_stream(d2s_handle h, d2s_stream_t stream);
 /* Debug/parity taps: copy an internal activation (by name) to a caller buffer as fp32. */
 int d2s_debug_tap(d2s_handle h, const char *name, float *dst, size_t max_elems, size_t *n_elems, d2s_stream_t stream);
 size_t d2s_workspace_bytes(d2s_handle h);

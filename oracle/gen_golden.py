@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/depth.py) on CPU.
 
 Run in the build container only (the reference tree does not travel to the GPU box):
-    python -m oracle.gen_golden [warp] [post] [pre] [model] [e2e] [overlay]
+    python -m oracle.gen_golden [warp] [post] [pre] [model] [e2e] [overlay] [vda]
 Each fixture stores the seeded inputs, the parameters and the reference's outputs, plus the
 torch/transformers versions that produced them.  Test infrastructure only.
 """
@@ -284,12 +284,64 @@ def gen_overlay(depth_mod):
     print("overlay.npz written")
 
 
+VDA_CASE = dict(encoder="vits", seed=21, H=70, W=98, frames=40, keep=[0, 1, 2, 17, 31, 32, 33, 39])
+
+
+def vda_frames(seed, T, H, W):
+    """T correlated model inputs [T,1,3,H,W] (a drifting pattern + a little per-frame noise), regenerable from the seed."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    out = []
+    for t in range(T):
+        base = np.stack([np.sin((xx + 1.5 * t) / W * (4 + c)) * np.cos((yy - 0.7 * t) / H * (3 + c)) for c in range(3)], 0)
+        out.append((base * 1.5 + rng.normal(0, 0.1, (3, H, W))).astype(np.float32)[None])
+    return np.stack(out)
+
+
+def gen_vda(_unused):
+    """Streaming Video-Depth-Anything: the reference's own module (models/video_depth_anything/vda2_s.py) on CPU in fp32, seeded
+    weights (oracle/vda.py make_state_dict), 40 frames so that the 32-frame window wraps.  `fp32=True` disables autocast except for
+    one place the reference forces it (dpt_temporal.py:115-118, output_conv2 under autocast => bf16 on CPU); that forced autocast
+    is switched off here so that the golden is a precision reference."""
+    import contextlib
+    import types
+    from . import vda
+    from .ref_harness import REFERENCE_ROOT
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    if "easydict" not in sys.modules:      # dpt_temporal.py:19 imports easydict (absent here): attribute-dict stub
+        ed = types.ModuleType("easydict")
+
+        class EasyDict(dict):
+            def __init__(self, **kw):
+                super().__init__(**kw)
+                self.__dict__ = self
+        ed.EasyDict = EasyDict
+        sys.modules["easydict"] = ed
+    import models.video_depth_anything.dpt_temporal as dt
+    dt.maybe_autocast = lambda *a, **k: contextlib.nullcontext()
+    from models.video_depth_anything.vda2_s import VideoDepthAnything
+    c = VDA_CASE
+    enc = vda.ENCODERS[c["encoder"]]
+    m = VideoDepthAnything(encoder=c["encoder"], features=enc["features"], out_channels=enc["out_channels"]).eval()
+    assert [n for n, _ in vda.param_shapes(c["encoder"])] == list(m.state_dict().keys())
+    m.load_state_dict(vda.make_state_dict(c["encoder"], c["seed"]), strict=True)
+    frames = vda_frames(c["seed"], c["frames"], c["H"], c["W"])
+    out = {"versions": _versions()}
+    for t in range(c["frames"]):
+        d = m(pixel_values=torch.from_numpy(frames[t]), fp32=True)
+        if t in c["keep"]:
+            out[f"depth{t}"] = d.numpy()[0, 0]
+    print("vda golden", tuple(d.shape), float(d.min()), float(d.max()))
+    np.savez_compressed(os.path.join(GOLDEN, "vda.npz"), **out)
+
+
 def main(argv):
     os.makedirs(GOLDEN, exist_ok=True)
-    what = set(argv) or {"warp", "post", "pre", "model", "e2e", "overlay"}
+    what = set(argv) or {"warp", "post", "pre", "model", "e2e", "overlay", "vda"}
     depth_mod = load_reference("Small")
     g = globals()
-    for name in ["warp", "post", "pre", "model", "e2e", "overlay"]:
+    for name in ["warp", "post", "pre", "model", "e2e", "overlay", "vda"]:
         if name in what and f"gen_{name}" in g:
             g[f"gen_{name}"](depth_mod)
 
