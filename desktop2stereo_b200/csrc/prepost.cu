@@ -199,13 +199,59 @@ static int run_resize(const d2s_image *src, int h, int w, void *dst, int dst_dty
 // ------------------------------------------------------------------------------------------------
 constexpr int kSortCap = 8192;
 
-// Q1: strided subsample -> bitonic sort in shared memory -> k-th smallest / k-th largest  (depth.py:784-794, 849-858)
+// metric models (depth.py:837-841): inv = where(d > 0, 1 / clamp(d, 1e-12), d), each op rounded to CT
 template <typename IT, typename CT>
-__global__ void __launch_bounds__(1024) post_bounds_kernel(const IT *__restrict__ d, int n, int step, int ns, int k,
-                                                           float *__restrict__ bounds) {
+__device__ __forceinline__ float metric_inv(IT raw, bool &valid) {
+    const float x = round_to<CT>(to_f32<IT>(raw));
+    valid = x > 0.f;
+    return valid ? round_to<CT>(__fdiv_rn(1.0f, fmaxf(x, round_to<CT>(1e-12f)))) : x;
+}
+
+// Q1: strided subsample -> bitonic sort in shared memory -> k-th smallest / k-th largest  (depth.py:784-794, 849-858).
+// metric: the sample is taken from the COMPACTED list of valid (d > 0) inverted values, v = inv[valid]; vv = v[::step] with
+// step = ceil(len(v) / cap) — a block-wide scan gives every valid element its rank in v, so the strided pick is exact.
+template <typename IT, typename CT>
+__global__ void __launch_bounds__(1024) post_bounds_kernel(const IT *__restrict__ d, int n, int step, int ns, int k, int metric, int cap,
+                                                           double lo_q, float *__restrict__ bounds) {
     __shared__ float s[kSortCap];
-    for (int i = threadIdx.x; i < kSortCap; i += blockDim.x)
-        s[i] = i < ns ? round_to<CT>(to_f32<IT>(d[(size_t)i * step])) : INFINITY;
+    __shared__ int s_scan[1024];
+    __shared__ int s_meta[3];   // n valid, ns, k
+    int n_eff = n;
+    if (!metric) {
+        for (int i = threadIdx.x; i < kSortCap; i += blockDim.x)
+            s[i] = i < ns ? round_to<CT>(to_f32<IT>(d[(size_t)i * step])) : INFINITY;
+    } else {
+        const int chunk = (n + 1023) / 1024, i0 = min((int)threadIdx.x * chunk, n), i1 = min(i0 + chunk, n);
+        int cnt = 0;
+        for (int i = i0; i < i1; ++i) { bool v; metric_inv<IT, CT>(d[i], v); cnt += v ? 1 : 0; }
+        s_scan[threadIdx.x] = cnt;
+        for (int i = threadIdx.x; i < kSortCap; i += blockDim.x) s[i] = INFINITY;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {            // inclusive Hillis-Steele scan of the per-thread counts
+            int v = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int nv = s_scan[1023];
+            int st = 1, m = nv;
+            if (nv > cap) { st = (nv + cap - 1) / cap; m = (nv + st - 1) / st; }
+            int kk = (int)nearbyint(lo_q * (double)(m - 1)) + 1;
+            kk = kk < 1 ? 1 : kk; kk = kk > m ? m : kk;
+            s_meta[0] = nv; s_meta[1] = m; s_meta[2] = kk;
+            s_scan[1023] = st;   // (the last inclusive value is no longer needed: reuse the slot for the step)
+        }
+        __syncthreads();
+        const int st = s_scan[1023];
+        int rank = threadIdx.x == 0 ? 0 : (threadIdx.x == 1023 ? s_meta[0] - cnt : s_scan[threadIdx.x - 1]);
+        for (int i = i0; i < i1; ++i) {
+            bool v;
+            const float x = metric_inv<IT, CT>(d[i], v);
+            if (v) { if (rank % st == 0) s[rank / st] = x; ++rank; }
+        }
+        n_eff = s_meta[0]; ns = s_meta[1]; k = s_meta[2];
+    }
     __syncthreads();
     for (int size = 2; size <= kSortCap; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -221,7 +267,7 @@ __global__ void __launch_bounds__(1024) post_bounds_kernel(const IT *__restrict_
     }
     if (threadIdx.x == 0) {
         float lo, hi;
-        if (n <= 10) { lo = 0.f; hi = 0.f; }                 // depth.py:845-847
+        if (n_eff <= 10) { lo = 0.f; hi = 0.f; }             // depth.py:845-847
         else if (k >= ns) { lo = s[0]; hi = s[ns - 1]; }       // tail_count == n -> min/max
         else { lo = s[k - 1]; hi = s[ns - k]; }
         bounds[0] = lo; bounds[1] = hi;
@@ -231,12 +277,13 @@ __global__ void __launch_bounds__(1024) post_bounds_kernel(const IT *__restrict_
 // Q1 (normalise) + Q2 (gamma, foreground scale), per element, each op rounded to CT like ATen's opmath kernels
 template <typename IT, typename CT>
 __global__ void post_point_kernel(const IT *__restrict__ d, int n, const float *__restrict__ bounds, float gamma,
-                                  int fg_on, float fg_exp, float *__restrict__ out) {
+                                  int fg_on, float fg_exp, int metric, float *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float lo = bounds[0], hi = bounds[1];
     float denom = round_to<CT>(fmaxf(round_to<CT>(__fsub_rn(hi, lo)), 1e-6f));
-    float x = round_to<CT>(to_f32<IT>(d[i]));
+    bool valid;
+    float x = metric ? metric_inv<IT, CT>(d[i], valid) : round_to<CT>(to_f32<IT>(d[i]));
     float t = round_to<CT>(__fdiv_rn(round_to<CT>(__fsub_rn(x, lo)), denom));
     t = fminf(fmaxf(t, 0.f), 1.f);
     t = round_to<CT>(powf(t, gamma));
@@ -357,10 +404,10 @@ static int run_post(const d2s_post_params *p, d2s_stream_t st) {
     double lo_q = fmax(0.0, fmin(1.0, (double)p->percentile / 100.0));
     int k = (int)nearbyint(lo_q * (double)(ns - 1)) + 1;
     k = k < 1 ? 1 : k; k = k > ns ? ns : k;
-    D2S_LAUNCH((post_bounds_kernel<IT, CT>), 1, 1024, 0, st, (const IT *)p->depth_in, n, step, ns, k, bounds);
+    D2S_LAUNCH((post_bounds_kernel<IT, CT>), 1, 1024, 0, st, (const IT *)p->depth_in, n, step, ns, k, p->metric ? 1 : 0, p->subsample_cap, lo_q, bounds);
     int fg_on = fabs((double)p->foreground_scale) >= 1e-6;
     float fg_exp = (float)(1.0 / (1.0 + (double)p->foreground_scale));
-    D2S_LAUNCH((post_point_kernel<IT, CT>), ceil_div(n, 256), 256, 0, st, (const IT *)p->depth_in, n, bounds, p->gamma, fg_on, fg_exp, bufA);
+    D2S_LAUNCH((post_point_kernel<IT, CT>), ceil_div(n, 256), 256, 0, st, (const IT *)p->depth_in, n, bounds, p->gamma, fg_on, fg_exp, p->metric ? 1 : 0, bufA);
     BlurW bw = make_gauss<CT>(p->aa_strength);
     D2S_REQUIRE(bw.k <= 63, "d2s_postprocess: anti-alias kernel size %d too large", bw.k);
     float ema_w = (float)(1.0 - (double)p->ema_alpha);
@@ -465,7 +512,7 @@ extern "C" int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream) {
     D2S_REQUIRE(p && p->depth_in && p->H > 0 && p->W > 0, "d2s_postprocess: bad arguments");
     D2S_REQUIRE(p->out == nullptr || (p->out_h > 0 && p->out_w > 0), "d2s_postprocess: bad output size");
     D2S_REQUIRE(p->subsample_cap >= 1, "d2s_postprocess: subsample_cap");
-    if (p->metric) return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: metric-depth inversion (depth.py:837-841) not implemented");
+    D2S_REQUIRE(!p->metric || p->subsample_cap <= 8192, "d2s_postprocess: subsample_cap %d exceeds the sort capacity", p->subsample_cap);
     switch (p->in_dtype) {
         case D2S_F32: return run_post_ct<float>(p, stream);
         case D2S_F16: return run_post_ct<__half>(p, stream);

@@ -195,6 +195,34 @@ def gen_post(depth_mod):
     print(f"post.npz: {i} cases")
 
 
+POST_METRIC_CASES = [(0, 42, 70, "float32", 1), (1, 294, 518, "float32", 7), (2, 70, 70, "bfloat16", 1), (3, 3, 3, "float32", 1)]
+
+
+def synth_metric_depth(seed, H, W):
+    """Metric-depth-like map (metres) with invalid (<= 0) holes, regenerable from the seed."""
+    rng = np.random.default_rng(seed)
+    d = 0.5 + 4.0 * synth_depth(seed, H, W) / 4.0
+    d[rng.random((H, W)) < 0.07] = 0.0
+    d[H // 5: H // 4, W // 3: W // 2] = -1.0
+    return d.astype(np.float32)
+
+
+def gen_post_metric(depth_mod):
+    """post_process_depth with is_metric() true (depth.py:837-841: 1/d on d > 0, percentiles over the valid values only)."""
+    out = {"versions": _versions()}
+    old = depth_mod._IS_METRIC
+    depth_mod._IS_METRIC = True
+    try:
+        for (seed, H, W, dt, sub) in POST_METRIC_CASES:
+            raw = torch.from_numpy(synth_metric_depth(seed, H, W)).to(getattr(torch, dt))
+            pp = depth_mod.post_process_depth(raw.clone())
+            out[f"m{seed}"] = pp.float().numpy()[::sub, ::sub]
+    finally:
+        depth_mod._IS_METRIC = old
+    np.savez_compressed(os.path.join(GOLDEN, "post_metric.npz"), **out)
+    print("post_metric.npz written")
+
+
 TINY = dict(hidden=128, layers=4, heads=2, out_indices=[1, 2, 3, 4], neck=[24, 48, 96, 192], fusion=64)
 MODEL_CASES = [  # (name, variant, tiny cfg, seed, B, H, W, stored stride)
     ("tiny_70x98", "Small", TINY, 3, 2, 70, 98, 1),
@@ -338,10 +366,10 @@ def gen_vda(_unused):
 
 def main(argv):
     os.makedirs(GOLDEN, exist_ok=True)
-    what = set(argv) or {"warp", "post", "pre", "model", "e2e", "overlay", "vda"}
+    what = set(argv) or {"warp", "post", "pre", "model", "e2e", "overlay", "vda", "post_metric"}
     depth_mod = load_reference("Small")
     g = globals()
-    for name in ["warp", "post", "pre", "model", "e2e", "overlay", "vda"]:
+    for name in ["warp", "post", "pre", "model", "e2e", "overlay", "vda", "post_metric"]:
         if name in what and f"gen_{name}" in g:
             g[f"gen_{name}"](depth_mod)
 

@@ -77,3 +77,18 @@ def _check_post(post, fg, aa, tol):
             # ATen's CPU bilinear kernel differs by 1 ulp between its vector body and scalar tail, which move with
             # the thread count (the reference pins 1 thread, depth.py:19): floating-point stage, tolerance 1 ulp.
             assert np.allclose(up.float().numpy()[::sub * 3, ::sub * 3], post[f"post{i}_f{f}_up"], rtol=0, atol=tol[dt]), (i, f, "up")
+
+
+def test_post_metric_oracle_matches_reference(golden_dir):
+    """Metric models: 1/d on the valid mask, percentile bounds over the compacted valid values (depth.py:837-858)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import prepost as opp
+    from oracle.gen_golden import POST_METRIC_CASES, synth_metric_depth
+    g = np.load(os.path.join(golden_dir, "post_metric.npz"))
+    for (seed, H, W, dt, sub) in POST_METRIC_CASES:
+        raw = torch.from_numpy(synth_metric_depth(seed, H, W)).to(getattr(torch, dt))
+        got = opp.post_process_depth(raw, 0.05, 4.0, metric=True).float().numpy()[::sub, ::sub]
+        tol = 2e-6 if dt == "float32" else 8e-3      # 1 bf16 ulp at 1.0
+        assert np.abs(got - g[f"m{seed}"]).max() <= tol, (seed, np.abs(got - g[f"m{seed}"]).max())

@@ -124,3 +124,23 @@ def test_postprocess_edge_cases(cuda_device):
     tiny = torch.rand(2, 5, device=cuda_device)                  # numel <= 10 -> dmin = dmax = 0
     out = pp(tiny, use_temporal_smooth=False)
     assert (out - opp.post_process_depth(tiny, 0.0, 0.0)).abs().max().item() <= 2e-6
+
+
+def test_postprocess_metric_vs_golden_and_oracle(cuda_device, golden_dir):
+    """Metric models (depth.py:837-858): 1/d on d > 0, percentile bounds over the compacted valid values."""
+    from desktop2stereo_b200.prepost import PostProcessor
+    from oracle.gen_golden import POST_METRIC_CASES, synth_metric_depth
+    g = np.load(os.path.join(golden_dir, "post_metric.npz"))
+    for (seed, H, W, dt, sub) in POST_METRIC_CASES:
+        tdt = getattr(torch, dt)
+        raw = torch.from_numpy(synth_metric_depth(seed, H, W)).to(tdt).to(cuda_device)
+        pp = PostProcessor(foreground_scale=0.05, aa_strength=4.0, metric=True)
+        out = pp(raw, use_temporal_smooth=False)
+        tol = 2e-6 if dt == "float32" else 1.6e-2
+        assert np.abs(out.float().cpu().numpy()[::sub, ::sub] - g[f"m{seed}"]).max() <= tol, (seed, dt)
+        ref = opp.post_process_depth(raw, 0.05, 4.0, metric=True)        # the same ops through ATen's CUDA kernels
+        assert (out.float() - ref.float()).abs().max().item() <= tol
+    # all-invalid frame: no valid value -> bounds 0/0 -> denom 1e-6 -> everything clamps to 0 (then gamma / fg-scale of 0)
+    bad = torch.full((20, 30), -1.0, device=cuda_device)
+    out = PostProcessor(foreground_scale=0.05, aa_strength=4.0, metric=True)(bad, use_temporal_smooth=False)
+    assert torch.equal(out, opp.post_process_depth(bad, 0.05, 4.0, metric=True))
