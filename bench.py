@@ -140,6 +140,13 @@ def run_reference(args):
     return 0
 
 
+WORKLOADS = {
+    # name: (variant, frame h, frame w, frames per engine call, description)
+    "base1080": ("Base", 1080, 1920, 1, "BASELINE.json configs[1]: DA-V2-Base, 1080p BGRA batch=1 -> Full-SBS (model input 294x518, 778 tokens)"),
+    "large4k": ("Large", 2160, 3840, 8, "BASELINE.json configs[2]: DA-V2-Large, 4K BGRA batch=8 -> Full-SBS (model input 8 x 294x518, 6224 token rows)"),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,10 +155,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
-    ap.add_argument("--slots", type=int, default=4, help="frames in flight (CUDA streams) in the pipelined legs")
+    ap.add_argument("--slots", type=int, default=8, help="frames in flight (CUDA streams) in the pipelined legs")
+    ap.add_argument("--workload", default="base1080", choices=sorted(WORKLOADS),
+                    help="base1080 is the headline (configs[1]); large4k (configs[2]) is an extra measurement, not the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "large4k":
+        return run_large4k(args)
 
     import numpy as np
     import torch
@@ -168,24 +179,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from desktop2stereo_b200 import _lib, depth
-    from desktop2stereo_b200.engine import B200Engine
     from desktop2stereo_b200.stereo import make_sbs_core
-    from desktop2stereo_b200.weights import config_from_hf, pack_state_dict
     L = _lib.lib()
     warmup = max(args.warmup, 3)
-
-    # ---- weights: rank 0 packs, one NCCL broadcast over NVLink, every rank builds its own engine ----
-    from transformers import DepthAnythingConfig
-    from desktop2stereo_b200 import sharding
-    blob = cfg_json = None
-    if rank == 0:
-        model = build_hf_model()
-        blob = pack_state_dict(model.state_dict(), config_from_hf(model.config))
-        cfg_json = model.config.to_json_string()
-        del model
-    blob, cfg_json = sharding.broadcast_weights(blob, cfg_json, src=0, device=dev)
-    cfg = config_from_hf(DepthAnythingConfig.from_dict(json.loads(cfg_json)))
-    engine = B200Engine(blob, cfg, dev, out_dtype=torch.float16)
+    engine, cfg = build_engine(VARIANT, rank, world, dev)
     depth.init(engine=engine, device=dev)
 
     # ---- synthetic frames: a ring larger than L2 so no timed iteration re-reads a cached frame ----
@@ -216,10 +213,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    def stage_means(trace):
+    def stage_stats(trace):
+        """per-stage device time from the events recorded on each frame's stream: median (robust to a host hiccup) and mean"""
         torch.cuda.synchronize()
         st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in trace])
-        return dict(zip(["process", "predict_depth", "warp"], st.mean(0).tolist()))
+        names = ["process", "predict_depth", "warp"]
+        return dict(zip(names, np.median(st, 0).tolist())), dict(zip(names, st.mean(0).tolist()))
 
     # ---- (1) serial, one stream: the drop-in calls back to back; isolates per-stage device times ----
     serial_trace = []
@@ -249,7 +248,7 @@ def main():
     serial_trace.clear()
     n_serial = min(args.steps, 100)
     ms_serial = timed(serial_device, n_serial)
-    serial_stage_ms = stage_means(serial_trace)
+    serial_stage_ms, serial_stage_mean = stage_stats(serial_trace)
     serial_e2e(range(warmup))
     ms_serial_e2e = timed(serial_e2e, n_serial)
 
@@ -260,8 +259,8 @@ def main():
         for _ in pipe.run((frames[i % RING] for i in idx), host=False):
             pass
 
-    def pipe_e2e(idx):
-        for res in pipe.run((host_np[i % 4] for i in idx), host=True):
+    def pipe_e2e(idx, p=pipe):
+        for res in p.run((host_np[i % 4] for i in idx), host=True):
             pass
         return res
 
@@ -276,7 +275,7 @@ def main():
     torch.cuda.profiler.stop()
     launches = L.d2s_launch_count() - launches0
     clk = clocks.stop()
-    stage_ms = stage_means(pipe.trace)   # events recorded on each frame's stream INSIDE the timed region
+    stage_ms, _ = stage_stats(pipe.trace)   # events recorded on each frame's stream INSIDE the timed region (streams overlap)
     pipe.trace = None
     fps = world * args.steps / (ms / 1e3)
 
@@ -286,28 +285,35 @@ def main():
     fps_e2e = world * args.steps / (ms_e2e / 1e3)
     h2d, d2h = H * W * 4, H * 2 * W * 3 * 4
 
+    # the same end-to-end loop with the 4x smaller u8 frame packed on the device (not the reference's return type)
+    pipe8 = StereoPipeline(depth_slots=args.slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, out_dtype=torch.uint8)
+    res8 = pipe_e2e(range(max(warmup, 2 * args.slots)), pipe8)
+    assert res8.shape == (H, 2 * W, 3) and res8.dtype == np.uint8
+    ms_e2e8 = timed(lambda idx: pipe_e2e(idx, pipe8), args.steps)
+
     # ---- rooflines (denominators: MEASURED_PEAKS.json, else the profiling guide's fallback) ----
-    peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0}, "fallback"
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); src = "measured"
-    except Exception:
-        pass
-    # warp kernel: fp16 CHW rgb in (6 B/px) + fp16 depth in (2 B/px) + fp32 HWC Full-SBS out (24 B/px)
+    peaks, src = load_peaks()
+    # warp kernel: fp16 CHW rgb in (6 B/px) + fp16 depth in (2 B/px) + fp32 HWC Full-SBS out (24 B/px); timed alone (serial leg:
+    # one frame at a time on one stream, CUDA events on that stream) so the duration is the kernel's, not a share of a busy GPU
     warp_bytes = H * W * (6 + 2 + 24)
-    warp_gbs = warp_bytes / (stage_ms["warp"] * 1e-3) / 1e9
-    # the network is replayed as ONE CUDA-graph launch per frame; its kernels are timed together via predict_depth
+    warp_gbs = warp_bytes / (serial_stage_ms["warp"] * 1e-3) / 1e9
+    # the network is replayed as ONE CUDA-graph launch per frame (~140 kernels, the tcgen05 GEMM is ~60 % of its time):
+    #   isolated: duration of one launch alone on the GPU (serial leg) -> batch-1 latency view
+    #   in the timed region: `slots` launches overlap, so GPU time per launch = timed region / launches
     Hm, Wm = 294, 518
     gflop = model_flops(cfg, Hm, Wm) / 1e9
-    net_tflops = gflop / (stage_ms["predict_depth"] * 1e-3) / 1e3
-    dominant = max(stage_ms, key=stage_ms.get)
-    roofline_warp = {"kernel": "warp_sbs_kernel", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": src,
-                     "bytes_per_launch": warp_bytes, "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS"}
-    roofline_net = {"kernel": "depth network (one graph launch: preprocess + ViT-B + DPT + postprocess)", "bound": "tensor",
-                    "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": src,
-                    "gflop_per_launch": gflop}
-    roofline = roofline_warp if dominant == "warp" else roofline_net
+    net_tflops_iso = gflop / (serial_stage_ms["predict_depth"] * 1e-3) / 1e3
+    net_tflops = gflop * args.steps / (ms * 1e-3) / 1e3
+    roofline_warp = {"kernel": "warp_sbs_fast_kernel", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "bytes_per_launch": warp_bytes,
+                     "duration_ms": serial_stage_ms["warp"], "timed": "alone on the GPU (serial leg), CUDA events on its stream, median of %d" % n_serial,
+                     "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS"}
+    roofline_net = {"kernel": "depth network, one graph launch per frame (preprocess + ViT-B + DPT on gemm_tc_kernel/tcgen05 + postprocess)",
+                    "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": src, "gflop_per_launch": gflop,
+                    "duration_ms": ms / args.steps, "timed": "timed region / launches with %d launches in flight" % args.slots,
+                    "isolated": {"achieved": net_tflops_iso, "frac": net_tflops_iso / peaks["bf16_tflops_sustained"],
+                                 "duration_ms": serial_stage_ms["predict_depth"], "note": "one launch alone on the GPU: batch-1 is latency-bound"}}
 
     line = {
         "metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": fps, "unit": "frames/s", "n_gpus": world,
@@ -317,13 +323,17 @@ def main():
                    "l2": f"ring of {RING} distinct frames ({RING * H * W * 4 / 1e6:.0f} MB) > 126 MB L2", "parallelism": f"frames sharded x{world}; {args.slots} frames in flight per GPU",
                    "weights": "seeded random init, one NCCL broadcast at init" if world > 1 else "seeded random init"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps,
-                "api": f"StereoPipeline({args.slots} frames in flight): pinned BGRA frame -> process -> predict_depth -> make_sbs -> float32 HWC host frame"},
+                "ms_per_step": ms_e2e / args.steps, "pcie_gbs": (h2d + d2h) * fps_e2e / world / 1e9,
+                "api": f"StereoPipeline({args.slots} frames in flight): pinned BGRA frame -> process -> predict_depth -> make_sbs -> float32 HWC host frame",
+                "note": "bounded by the device->host copy of the reference-faithful float32 frame (49.8 MB/frame)"},
+        "e2e_u8": {"value": world * args.steps / (ms_e2e8 / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * 2 * W * 3,
+                   "note": "same loop, uint8 HWC frame packed by the warp kernel (4x fewer bytes over PCIe); not the reference's return dtype"},
         "gpu_launches": int(launches), "clocks": clk, "stage_ms": stage_ms,
-        "serial": {"note": "same calls, one frame at a time on one stream (latency view)", "steps": n_serial,
+        "serial": {"note": "same calls, one frame at a time on one stream (latency view); stage_ms = medians", "steps": n_serial,
                    "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
-                   "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms},
-        "roofline": roofline, "roofline_warp": roofline_warp, "roofline_net": roofline_net,
+                   "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms,
+                   "stage_ms_mean": serial_stage_mean},
+        "roofline": roofline_net, "roofline_warp": roofline_warp, "roofline_net": roofline_net,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -334,6 +344,105 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def load_peaks():
+    peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); src = "measured"
+    except Exception:
+        pass
+    return peaks, src
+
+
+def build_engine(variant, rank, world, dev):
+    """rank 0 packs the seeded weights, one NCCL broadcast over NVLink, every rank builds its own engine"""
+    import torch
+    from transformers import DepthAnythingConfig
+    from desktop2stereo_b200 import sharding
+    from desktop2stereo_b200.engine import B200Engine
+    from desktop2stereo_b200.weights import config_from_hf, pack_state_dict
+    blob = cfg_json = None
+    if rank == 0:
+        model = build_hf_model(variant)
+        blob = pack_state_dict(model.state_dict(), config_from_hf(model.config))
+        cfg_json = model.config.to_json_string()
+        del model
+    blob, cfg_json = sharding.broadcast_weights(blob, cfg_json, src=0, device=dev)
+    cfg = config_from_hf(DepthAnythingConfig.from_dict(json.loads(cfg_json)))
+    return B200Engine(blob, cfg, dev, out_dtype=torch.float16), cfg
+
+
+def run_large4k(args):
+    """configs[2]: DA-V2-Large, 8 x 4K frames per engine call -> 8 Full-SBS frames.  Extra measurement (M = 6224 token rows is
+    where the tcgen05 GEMM is tensor-bound rather than latency-bound); one step = one batch of 8 frames."""
+    import numpy as np
+    import torch
+    from desktop2stereo_b200 import _lib
+    from desktop2stereo_b200.prepost import PostProcessor, preprocess, process
+    from desktop2stereo_b200.stereo import make_sbs_core
+    variant, h, w, B, desc = WORKLOADS["large4k"]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    engine, cfg = build_engine(variant, 0, 1, dev)
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(SEED)
+    RING = 2                                   # 2 x 8 x 33 MB = 531 MB of distinct frames > L2
+    frames = [[torch.randint(0, 256, (h, w, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(B)] for _ in range(RING)]
+    posts = [PostProcessor() for _ in range(B)]    # 8 concurrent streams: one EMA state each
+    batch = torch.empty((B, 3, 294, 518), dtype=torch.float32, device=dev)
+    outs = [torch.empty((h, 2 * w, 3), dtype=torch.float32, device=dev) for _ in range(B)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    trace = []
+
+    def step(i):
+        fr = frames[i % RING]
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        rgbs = [process(f, h) for f in fr]
+        for b, rgb in enumerate(rgbs):
+            preprocess(rgb, 518, 14, out=batch[b:b + 1])
+        e[1].record()
+        raw = engine(batch)
+        e[2].record()
+        for b in range(B):
+            d = posts[b](raw[b], out_size=(h, w))
+            make_sbs_core(rgbs[b], d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC", out=outs[b])
+        e[3].record()
+        trace.append(e)
+
+    warmup = max(args.warmup, 3)
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    trace.clear()
+    clocks = ClockSampler(dev.index or 0); clocks.start()
+    l0 = L.d2s_launch_count()
+    s, e = ev(), ev()
+    s.record()
+    for i in range(args.steps):
+        step(i)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    clk = clocks.stop()
+    st = np.median(np.array([[t[j].elapsed_time(t[j + 1]) for j in range(3)] for t in trace]), 0)
+    peaks, src = load_peaks()
+    gflop = B * model_flops(cfg, 294, 518) / 1e9
+    net_tf = gflop / (st[1] * 1e-3) / 1e3
+    line = {"metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": B * args.steps / (ms / 1e3), "unit": "frames/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
+            "config": {"workload": desc, "l2": "2 batches of 8 distinct 4K frames (531 MB) > 126 MB L2", "parallelism": "one stream, batch of 8 per engine call"},
+            "gpu_launches": int(L.d2s_launch_count() - l0), "clocks": clk,
+            "stage_ms": {"process+preprocess x8": float(st[0]), "engine (batch 8)": float(st[1]), "postprocess+warp x8": float(st[2])},
+            "roofline": {"kernel": "depth network, one graph launch per batch of 8 (ViT-L + DPT on gemm_tc_kernel/tcgen05)", "bound": "tensor",
+                         "achieved": net_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": net_tf / peaks["bf16_tflops_sustained"],
+                         "traffic": None, "peak_source": src, "gflop_per_launch": gflop, "duration_ms": float(st[1])},
+            "roofline_warp": {"kernel": "warp_sbs_fast_kernel x8 (+ postprocess x8)", "bound": "hbm", "bytes_per_launch": h * w * 32,
+                              "note": "stage time covers 8 post-process chains and 8 warp launches"}}
+    print(json.dumps(line))
     return 0
 
 
