@@ -208,8 +208,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         }
         // stage the bias while the main loop runs (the epilogue warps have nothing else to do yet)
         {
-            const int t = threadIdx.x - 64, n = tile_n * BN + t;
-            if (t < BN) s_bias[t] = (e.bias && n < g.N) ? __ldg(e.bias + n) : 0.f;
+            for (int t = threadIdx.x - 64; t < BN; t += 128) {
+                const int n = tile_n * BN + t;
+                s_bias[t] = (e.bias && n < g.N) ? __ldg(e.bias + n) : 0.f;
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         const bool fixup = g.splits > 1;   // split-K: this CTA only parks its partial sums; see step 2 below
@@ -337,6 +339,7 @@ typedef void (*GemmKernel)(const GemmArgs);
 struct Variant { int bn, act, mode; GemmKernel fn; };
 #define D2S_V(bn, act, mode) {bn, act, mode, gemm_tc_kernel<bn, act, mode>}
 static const Variant kVariants[] = {
+    D2S_V(256, ACT_NONE, MODE_C16), D2S_V(256, ACT_RELU, MODE_C16), D2S_V(256, ACT_GELU, MODE_C16), D2S_V(256, ACT_NONE, MODE_X32),
     D2S_V(128, ACT_NONE, MODE_C16), D2S_V(128, ACT_RELU, MODE_C16), D2S_V(128, ACT_GELU, MODE_C16), D2S_V(128, ACT_NONE, MODE_X32),
     D2S_V(64, ACT_NONE, MODE_C16),  D2S_V(64, ACT_RELU, MODE_C16),  D2S_V(64, ACT_GELU, MODE_C16),  D2S_V(64, ACT_NONE, MODE_X32),
     D2S_V(32, ACT_NONE, MODE_C16),  D2S_V(32, ACT_RELU, MODE_C16),  D2S_V(32, ACT_RELU, MODE_HEAD), D2S_V(32, ACT_NONE, MODE_X32),
@@ -347,8 +350,6 @@ static int epi_mode(const GemmEpi &e) { return e.w3 ? MODE_HEAD : (e.x32 ? MODE_
 static std::once_flag g_once;
 static int g_init_rc = D2S_OK;
 constexpr size_t kMaxSmem = 227 * 1024;
-
-template <int BN> static size_t smem_for(int stages) { return (size_t)stages * (kABytes + BN * BK * 2) + (2 * stages + 1) * 8 + 32 + 512 + 1024; }
 
 int gemm_init() {
     std::call_once(g_once, [] {
@@ -393,11 +394,21 @@ static int encode_nhwc(CUtensorMap *m, const void *base, const ConvGeom &g, int 
     return D2S_OK;
 }
 
-static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
-
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+// Tile width.  The main loop is bound by what one SM can pull from L2 (the whole chip moves ~12 TB/s from L2, i.e. ~43 B/clk per
+// SM when every SM streams): a 128 x 128 tile ingests 32 KB per 2.1 MFLOP k-block = 64 FLOP/B -> ~0.77 PFLOP/s chip-wide, which is
+// what the kernel measures (0.80-0.86).  A 128 x 256 tile ingests 48 KB per 4.2 MFLOP = 85 FLOP/B.  It is used when the problem has
+// enough 256-wide tiles to fill every SM (large batches; +16 % at M = 6224, profiles/r1_gemm_microbench.txt); small problems keep 128-wide tiles for parallelism (and split-K).
+static int pick_bn(int N, int mtiles) {
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    const int mode = env_int("D2S_GEMM_BN256", 1);    // 0 never, 1 heuristic, 2 whenever N allows
+    if (mode && N % 256 == 0 && (mode == 2 || (long long)mtiles * (N / 256) >= kNumSMs)) return 256;
+    return 128;
 }
 
 // Choose the split-K factor and the ring depth.  Most of this network's GEMMs are small (M = 778 tokens, or a few
@@ -410,8 +421,9 @@ static void finish_plan(GemmPlan *p) {
     const bool x32 = epi_mode(e) == MODE_X32;
     int splits = 1;
     const int max_splits = min(env_int("D2S_GEMM_MAX_SPLITS", 8), 8);   // the splits of a tile form one cluster: portable maximum 8
-    if (epi_mode(e) == MODE_HEAD) {
-        splits = 1;                                    // the fused 1x1 head reduces over all N columns inside one thread
+    if (epi_mode(e) == MODE_HEAD || p->BN == 256) {
+        splits = 1;                                    // the fused 1x1 head reduces over all N columns inside one thread; 256-wide
+                                                       // tiles are only chosen for problems that fill the GPU without splitting
     } else if (x32) {
         splits = kNumSMs / base;                       // bias-only epilogue into the fp32 stream: cheap fix-up
         if (splits > p->kblocks / 3) splits = p->kblocks / 3;
@@ -435,8 +447,9 @@ static void finish_plan(GemmPlan *p) {
     // 96 KB ring lets two CTAs share an SM so that one CTA's prologue/epilogue overlaps another's main loop — measured +35 %
     // frames/s with several frames in flight, no change in single-frame latency (profiles/r1_sweep_ring_depth.txt).
     { int ms = env_int("D2S_GEMM_MAX_STAGES", 3); if (ms >= 2 && stages > ms) stages = ms; }
+    if (p->BN == 256) { stages = env_int("D2S_GEMM_BN256_STAGES", 2); if (stages < 2) stages = 2; if (stages > 4) stages = 4; }   // 2 x 48 KB: two CTAs (2 x 256 TMEM columns) per SM
     p->stages = stages;
-    p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 32 + 512 + 1024;
+    p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 32 + (size_t)p->BN * 4 + 16 + 1024;
     if (env_int("D2S_VERBOSE", 0))
         fprintf(stderr, "[d2s gemm] %s M=%d N=%d K=%d BN=%d grid=(%d,%d,%d) kblocks=%d kb/split=%d stages=%d smem=%zu %s\n", p->conv ? "conv" : "lin ",
                 p->M, p->N, p->K, p->BN, p->grid.x, p->grid.y, p->grid.z, p->kblocks, p->kb_per_split, stages, p->smem,
@@ -459,7 +472,7 @@ int gemm_plan_linear(GemmPlan *p, const __half *A, int lda, const __half *Bw, in
     if ((rc = check_epi(epi, N))) return rc;
     D2S_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     *p = GemmPlan{};
-    p->M = M; p->N = N; p->K = K; p->BN = pick_bn(N); p->conv = 0; p->epi = epi;
+    p->M = M; p->N = N; p->K = K; p->BN = pick_bn(N, ceil_div(M, BM)); p->conv = 0; p->epi = epi;
     p->kblocks = ceil_div(K, BK);
     if ((rc = encode_2d(&p->tmA, A, M, K, lda, BM))) return rc;
     if ((rc = encode_2d(&p->tmB, Bw, N, K, ldb, p->BN))) return rc;
@@ -477,7 +490,7 @@ int gemm_plan_conv3x3(GemmPlan *p, const __half *A, const ConvGeom &g, const __h
     p->conv = 1; p->B = g.B; p->H = g.H; p->W = g.W; p->Cp = g.Cp;
     p->TW = g.W <= 8 ? 8 : 16; p->TH = BM / p->TW;
     p->tiles_x = ceil_div(g.W, p->TW); p->tiles_y = ceil_div(g.H, p->TH);
-    p->N = N; p->K = 9 * g.Cp; p->BN = pick_bn(N); p->epi = epi;
+    p->N = N; p->K = 9 * g.Cp; p->BN = pick_bn(N, g.B * p->tiles_x * p->tiles_y); p->epi = epi;
     p->M = g.B * p->tiles_x * p->tiles_y * BM;
     p->kblocks = 9 * (g.Cp / BK);
     if ((rc = encode_nhwc(&p->tmA, A, g, p->TW, p->TH))) return rc;

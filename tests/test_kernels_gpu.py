@@ -22,6 +22,7 @@ def _act(x, name):
     (128, 128, 64, "none"), (128, 128, 256, "none"), (778, 2304, 768, "none"), (778, 3072, 768, "gelu"),
     (300, 96, 768, "relu"), (1000, 32, 576, "none"), (64, 64, 640, "none"), (1554, 384, 384, "none"),
     (6224, 1024, 4096, "none"), (37, 48, 128, "none"),
+    (6224, 1024, 512, "gelu"), (6224, 3072, 256, "relu"), (5000, 2048, 320, "none"),     # enough tiles for the 128 x 256 tile variant
 ])
 def test_gemm_tcgen05(cuda_device, M, N, K, act):
     from desktop2stereo_b200 import _lib
@@ -36,6 +37,21 @@ def test_gemm_tcgen05(cuda_device, M, N, K, act):
     err = (Cc.float() - ref).abs().max().item()
     assert torch.isfinite(Cc).all()
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), (M, N, K, err)
+
+
+def test_gemm_residual_stream_wide_tiles(cuda_device):
+    """The 128 x 256 tile variant on the fp32-stream epilogue (M large enough for the heuristic to pick it)."""
+    from desktop2stereo_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(6)
+    M, N, K = 6224, 1024, 1024
+    A = (torch.randn(M, K, generator=g) * 0.5).half().to(cuda_device)
+    Bw = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).half().to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    X = torch.randn(M, N, generator=g).to(cuda_device)
+    ref = X + (A.float() @ Bw.float().t() + bias)
+    _lib.check(_lib.lib().d2s_debug_gemm(A.data_ptr(), Bw.data_ptr(), bias.data_ptr(), None, M, N, K, 0, X.data_ptr(),
+                                         _stream(cuda_device)), "d2s_debug_gemm")
+    assert (X - ref).abs().max().item() <= 1e-3
 
 
 def test_gemm_residual_stream(cuda_device):

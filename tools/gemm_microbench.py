@@ -41,8 +41,18 @@ def bench(M, N, K, x32=False, interleave=False, iters=50):
 
 
 for (M, N, K, x32) in [(778, 2304, 768, False), (778, 3072, 768, False), (778, 768, 768, True), (778, 768, 3072, True),
-                        (128, 128, 768, False), (128, 128, 64, False), (6224, 3072, 1024, False), (6224, 1024, 4096, True)]:
+                        (128, 128, 768, False), (128, 128, 64, False)]:
     a = bench(M, N, K, x32)
     b = bench(M, N, K, x32, interleave=True)
     fl = 2 * M * N * K
     print(f"M={M} N={N} K={K} x32={x32}: back-to-back {a:7.1f} us ({fl / a / 1e6:7.1f} TFLOP/s)   interleaved with a 0-smem kernel {b:7.1f} us")
+# tile width at tensor-bound sizes: 128-wide vs 256-wide tiles (and ring depth for the latter)
+for (M, N, K, x32) in [(6224, 3072, 1024, False), (6224, 4096, 1024, False), (6224, 1024, 4096, True), (6224, 1024, 1024, True), (8192, 8192, 8192, False)]:
+    fl = 2 * M * N * K
+    res = []
+    for bn256, nst in ((0, 0), (2, 2), (2, 3), (2, 4)):
+        os.environ["D2S_GEMM_BN256"] = str(bn256)
+        os.environ["D2S_GEMM_BN256_STAGES"] = str(nst or 2)
+        a = bench(M, N, K, x32, iters=20)
+        res.append(f"{'BN128' if not bn256 else f'BN256/{nst}st'} {a:7.1f} us {fl / a / 1e6:6.0f} TF/s")
+    print(f"M={M} N={N} K={K} x32={x32}: " + " | ".join(res))
