@@ -260,7 +260,7 @@ def main():
             pass
 
     def pipe_e2e(idx, p=pipe):
-        for res in p.run((host_np[i % 4] for i in idx), host=True):
+        for res in p.run((host_frames[i % 4] for i in idx), host=True):   # pinned host frames -> H2D inside the timed region
             pass
         return res
 

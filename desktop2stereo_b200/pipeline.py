@@ -114,7 +114,12 @@ class StereoPipeline:
 
     def run(self, frames, host: bool = True):
         """Generator: keeps the pipeline full while iterating `frames`; yields results in order."""
-        submit = self.submit if host else self.submit_device
+        def submit(f):
+            if not host:
+                return self.submit_device(f)
+            if isinstance(f, torch.Tensor) and f.is_pinned():
+                return self.submit_pinned(f)          # already in pinned host memory: no staging copy on the host
+            return self.submit(f)
         for f in frames:
             if len(self.pending) == len(self.slots):
                 yield self.result(host=host)
