@@ -14,7 +14,7 @@ KEYS = [
     ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput %"),
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput % (alt)"),
-    ("lts__t_bytes.sum", "L2 bytes"), ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+    ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"), ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("sm__inst_executed.sum", "warp insts"), ("smsp__inst_executed.sum", "warp insts (smsp)"),
     ("sm__inst_issued.avg.pct_of_peak_sustained_active", "issue slots busy %"),
@@ -36,7 +36,8 @@ KEYS = [
 
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # accepts an .ncu-rep, or the CSV that `ncu -i x.ncu-rep --page raw --csv` wrote on the GPU box (reports are too big to bring back)
+    out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
