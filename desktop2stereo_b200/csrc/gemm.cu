@@ -21,7 +21,7 @@ constexpr int kGemmThreads = 192;
 struct GemmArgs {
     CUtensorMap tmA, tmB;
     int M, N, kblocks, stages;
-    int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y;
+    int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y, mtiles;
     int splits, kb_per_split;   // split-K: blockIdx.z owns k-blocks [z*kb_per_split, ...)
     long long *trace;           // optional: clock64 stamps of CTA (0,0,0) phases (debug)
     GemmEpi epi;
@@ -94,10 +94,16 @@ __device__ __forceinline__ void epilogue8(const GemmEpi &e, float (&v)[8], const
     }
 }
 
-template <int BN, int ACT, int MODE>
+// PAIR = 1: two CTAs adjacent in M (grid x = M tiles, cluster dims (2,1,1)) compute a 256 x BN tile with cta_group::2 MMAs.  Each CTA keeps its own
+// 128 rows of A and HALF of the B tile (BN/2 rows) in shared memory and its own 128 x BN accumulator in TMEM, so a k-block costs a
+// CTA 16 KB (A) + BN/2 x 128 B (B) of L2->SM traffic instead of 16 KB + BN x 128 B: 128 FLOP per ingested byte at BN = 256.
+// Both CTAs run a producer (their loads complete on the leader's mbarrier), the leader (even CTA) issues the MMAs and multicasts
+// the "slot free" / "accumulator ready" commits to both, both run the epilogue on their own rows.
+template <int BN, int ACT, int MODE, int PAIR = 0>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int kBBytes = BN * BK * 2;
+    constexpr int kBRows = PAIR ? BN / 2 : BN;        // rows of the B tile held by this CTA
+    constexpr int kBBytes = kBRows * BK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B needs 1024-B alignment
     const int stages = g.stages;
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     float *s_bias = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);  // this tile's bias (BN floats), staged by the epilogue warps during the main loop
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int tile_n = PAIR ? blockIdx.y : blockIdx.x, tile_m = PAIR ? blockIdx.x : blockIdx.y;   // a pair = two CTAs adjacent in x
     const bool tr = g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define D2S_STAMP(i) do { if (tr) g.trace[i] = clock64(); } while (0)
     if (threadIdx.x == 0) D2S_STAMP(0);
@@ -122,13 +128,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         ptx::fence_proxy_async();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, BN);
-        ptx::tmem_relinquish();
+        if (PAIR) { ptx::tmem_alloc_2sm(tmem_slot, BN); ptx::tmem_relinquish_2sm(); }
+        else { ptx::tmem_alloc(tmem_slot, BN); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync();   // the peer's barriers must be initialised before anything of ours can arrive on them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
     if (threadIdx.x == 0) D2S_STAMP(1);
 
     // conv tile -> (image, y0, x0)
@@ -155,15 +163,27 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
             uint8_t *a = smem;
             for (int i = 0; i < nkb; ++i) {
                 if (i >= stages) ptx::mbar_wait(&empty[s], ph ^ 1);   // the first pass over the ring finds every slot free
-                ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
-                if (g.conv) {
-                    int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-                    ptx::tma_load_4d(a, &g.tmA, &full[s], cc * BK, x0 + dx, y0 + dy, img);
-                    if (++cc == cchunks) { cc = 0; ++tap; }
+                if (PAIR) {
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kStageBytes);   // both CTAs' loads land on the leader's barrier
+                    if (g.conv) {
+                        int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        ptx::tma_load_4d_2sm(a, &g.tmA, &full[s], cc * BK, x0 + dx, y0 + dy, img);
+                        if (++cc == cchunks) { cc = 0; ++tap; }
+                    } else {
+                        ptx::tma_load_2d_2sm(a, &g.tmA, &full[s], (kb0 + i) * BK, tile_m * BM);
+                    }
+                    ptx::tma_load_2d_2sm(a + kABytes, &g.tmB, &full[s], (kb0 + i) * BK, tile_n * BN + (int)rank * kBRows);
                 } else {
-                    ptx::tma_load_2d(a, &g.tmA, &full[s], (kb0 + i) * BK, tile_m * BM);
+                    ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+                    if (g.conv) {
+                        int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        ptx::tma_load_4d(a, &g.tmA, &full[s], cc * BK, x0 + dx, y0 + dy, img);
+                        if (++cc == cchunks) { cc = 0; ++tap; }
+                    } else {
+                        ptx::tma_load_2d(a, &g.tmA, &full[s], (kb0 + i) * BK, tile_m * BM);
+                    }
+                    ptx::tma_load_2d(a + kABytes, &g.tmB, &full[s], (kb0 + i) * BK, tile_n * BN);
                 }
-                ptx::tma_load_2d(a + kABytes, &g.tmB, &full[s], (kb0 + i) * BK, tile_n * BN);
                 if (i == 0) D2S_STAMP(2);
                 a += kStageBytes;
                 if (++s == stages) { s = 0; ph ^= 1; a = smem; }
@@ -171,9 +191,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
             D2S_STAMP(3);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = ptx::make_idesc_f16(BM, BN, 0);
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (the leader CTA of a pair issues for both) =====
+            const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BN, 0);
             int s = 0;
             uint32_t ph = 0;
             uint32_t a_addr = ptx::smem_u32(smem);
@@ -184,13 +204,17 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                 const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr);
                 const uint64_t db = ptx::make_sw128_kmajor_desc(a_addr + kABytes);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 bytes: advance the start address by 2 (>>4)
-                    ptx::umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
-                ptx::umma_commit(&empty[s]);  // smem slot is free once these MMAs have read it
+                for (int k = 0; k < BK / 16; ++k) {  // UMMA_K = 16 fp16 = 32 bytes: advance the start address by 2 (>>4)
+                    if (PAIR) ptx::umma_f16_2sm(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                    else ptx::umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                }
+                if (PAIR) ptx::umma_commit_2sm(&empty[s], 3);   // slot s is free in BOTH CTAs once these MMAs have read it
+                else ptx::umma_commit(&empty[s]);             // smem slot is free once these MMAs have read it
                 a_addr += kStageBytes;
                 if (++s == stages) { s = 0; ph ^= 1; a_addr = ptx::smem_u32(smem); }
             }
-            ptx::umma_commit(tmem_full);      // accumulator complete
+            if (PAIR) ptx::umma_commit_2sm(tmem_full, 3);   // accumulators complete in both CTAs
+            else ptx::umma_commit(tmem_full);             // accumulator complete
             D2S_STAMP(5);
         }
     } else {
@@ -201,7 +225,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         long long orow;                        // output row (pixel / token) or -1
         if (g.conv) {
             int y = y0 + (r >> g.TW_shift), x = x0 + (r & (g.TW - 1));
-            orow = (y < g.H && x < g.W) ? ((long long)img * g.H + y) * g.W + x : -1;
+            orow = (y < g.H && x < g.W && tile_m < g.mtiles) ? ((long long)img * g.H + y) * g.W + x : -1;   // (pairs pad the grid to an even number of M tiles)
         } else {
             int m = tile_m * BM + r;
             orow = m < g.M ? m : -1;
@@ -316,11 +340,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         }
         ptx::cluster_sync();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
     }
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync();   // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
+    else __syncthreads();
     if (threadIdx.x == 0) D2S_STAMP(8);
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, BN);
+        if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, BN);
+        else ptx::tmem_dealloc(tmem_base, BN);
     }
     if (threadIdx.x == 32) D2S_STAMP(9);
 #undef D2S_STAMP
@@ -336,15 +362,18 @@ static EncodeTiledFn g_encode = nullptr;
 
 // the instantiations the network needs: (BN, activation, epilogue mode)
 typedef void (*GemmKernel)(const GemmArgs);
-struct Variant { int bn, act, mode; GemmKernel fn; };
-#define D2S_V(bn, act, mode) {bn, act, mode, gemm_tc_kernel<bn, act, mode>}
+struct Variant { int bn, act, mode, pair; GemmKernel fn; };
+#define D2S_V(bn, act, mode) {bn, act, mode, 0, gemm_tc_kernel<bn, act, mode, 0>}
+#define D2S_P(bn, act, mode) {bn, act, mode, 1, gemm_tc_kernel<bn, act, mode, 1>}
 static const Variant kVariants[] = {
+    D2S_P(256, ACT_NONE, MODE_C16), D2S_P(256, ACT_RELU, MODE_C16), D2S_P(256, ACT_GELU, MODE_C16), D2S_P(256, ACT_NONE, MODE_X32),
     D2S_V(256, ACT_NONE, MODE_C16), D2S_V(256, ACT_RELU, MODE_C16), D2S_V(256, ACT_GELU, MODE_C16), D2S_V(256, ACT_NONE, MODE_X32),
     D2S_V(128, ACT_NONE, MODE_C16), D2S_V(128, ACT_RELU, MODE_C16), D2S_V(128, ACT_GELU, MODE_C16), D2S_V(128, ACT_NONE, MODE_X32),
     D2S_V(64, ACT_NONE, MODE_C16),  D2S_V(64, ACT_RELU, MODE_C16),  D2S_V(64, ACT_GELU, MODE_C16),  D2S_V(64, ACT_NONE, MODE_X32),
     D2S_V(32, ACT_NONE, MODE_C16),  D2S_V(32, ACT_RELU, MODE_C16),  D2S_V(32, ACT_RELU, MODE_HEAD), D2S_V(32, ACT_NONE, MODE_X32),
 };
 #undef D2S_V
+#undef D2S_P
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 static int epi_mode(const GemmEpi &e) { return e.w3 ? MODE_HEAD : (e.x32 ? MODE_X32 : MODE_C16); }
 static std::once_flag g_once;
@@ -411,6 +440,15 @@ static int pick_bn(int N, int mtiles) {
     return 128;
 }
 
+// 2-CTA pairs (cta_group::2) for the 256-wide tiles.  D2S_GEMM_PAIR = 0 never, 2 whenever BN == 256, 1 (default): only when
+// the problem is several waves deep — with one tile per CTA (no persistent scheduler yet) a pair grid quantises worse than a
+// single-CTA grid at ~2 waves (M = 6224: 0.75-0.95 vs 0.89-0.96 PFLOP/s), and wins once there are many (8192^3: 1.26 vs 1.07).
+static int use_pair(int BN, int mtiles, int ntiles) {
+    const int mode = env_int("D2S_GEMM_PAIR", 1);
+    if (BN != 256 || mtiles < 2 || mode == 0) return 0;
+    return mode == 2 || (long long)mtiles * ntiles >= 8 * kNumSMs;
+}
+
 // Choose the split-K factor and the ring depth.  Most of this network's GEMMs are small (M = 778 tokens, or a few
 // hundred pixels at the coarse DPT levels): with one 128 x BN tile per CTA the grid covers a fraction of the 148 SMs and
 // the kernel time is a serial chain of k-blocks, each bounded by TMA latency / ring depth.  So: split K until the grid
@@ -437,7 +475,7 @@ static void finish_plan(GemmPlan *p) {
     p->splits = ceil_div(p->kblocks, p->kb_per_split);   // no empty split
     p->grid.z = p->splits;
 
-    const size_t stage = kABytes + (size_t)p->BN * BK * 2;
+    const size_t stage = kABytes + (size_t)(p->pair ? p->BN / 2 : p->BN) * BK * 2;
     const size_t budget = (base * p->splits > kNumSMs) ? kMaxSmem / 2 : kMaxSmem;   // two CTAs per SM only if needed
     int stages = (int)((budget - 2048) / stage);
     if (stages > p->kb_per_split) stages = p->kb_per_split;
@@ -447,7 +485,9 @@ static void finish_plan(GemmPlan *p) {
     // 96 KB ring lets two CTAs share an SM so that one CTA's prologue/epilogue overlaps another's main loop — measured +35 %
     // frames/s with several frames in flight, no change in single-frame latency (profiles/r1_sweep_ring_depth.txt).
     { int ms = env_int("D2S_GEMM_MAX_STAGES", 3); if (ms >= 2 && stages > ms) stages = ms; }
-    if (p->BN == 256) { stages = env_int("D2S_GEMM_BN256_STAGES", 2); if (stages < 2) stages = 2; if (stages > 4) stages = 4; }   // 2 x 48 KB: two CTAs (2 x 256 TMEM columns) per SM
+    if (p->BN == 256) {   // 2 x 48 KB (3 x 32 KB for a pair): two CTAs (2 x 256 TMEM columns) per SM
+        stages = env_int("D2S_GEMM_BN256_STAGES", p->pair ? 3 : 2); if (stages < 2) stages = 2; if (stages > 6) stages = 6;
+    }
     p->stages = stages;
     p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 32 + (size_t)p->BN * 4 + 16 + 1024;
     if (env_int("D2S_VERBOSE", 0))
@@ -474,9 +514,11 @@ int gemm_plan_linear(GemmPlan *p, const __half *A, int lda, const __half *Bw, in
     *p = GemmPlan{};
     p->M = M; p->N = N; p->K = K; p->BN = pick_bn(N, ceil_div(M, BM)); p->conv = 0; p->epi = epi;
     p->kblocks = ceil_div(K, BK);
+    p->mtiles = ceil_div(M, BM);
+    p->pair = use_pair(p->BN, p->mtiles, ceil_div(N, p->BN));
     if ((rc = encode_2d(&p->tmA, A, M, K, lda, BM))) return rc;
-    if ((rc = encode_2d(&p->tmB, Bw, N, K, ldb, p->BN))) return rc;
-    p->grid = dim3(ceil_div(N, p->BN), ceil_div(M, BM));
+    if ((rc = encode_2d(&p->tmB, Bw, N, K, ldb, p->pair ? p->BN / 2 : p->BN))) return rc;
+    p->grid = p->pair ? dim3((p->mtiles + 1) / 2 * 2, ceil_div(N, p->BN)) : dim3(ceil_div(N, p->BN), p->mtiles);
     finish_plan(p);
     return D2S_OK;
 }
@@ -491,11 +533,13 @@ int gemm_plan_conv3x3(GemmPlan *p, const __half *A, const ConvGeom &g, const __h
     p->TW = g.W <= 8 ? 8 : 16; p->TH = BM / p->TW;
     p->tiles_x = ceil_div(g.W, p->TW); p->tiles_y = ceil_div(g.H, p->TH);
     p->N = N; p->K = 9 * g.Cp; p->BN = pick_bn(N, g.B * p->tiles_x * p->tiles_y); p->epi = epi;
-    p->M = g.B * p->tiles_x * p->tiles_y * BM;
+    p->mtiles = g.B * p->tiles_x * p->tiles_y;
+    p->M = p->mtiles * BM;
     p->kblocks = 9 * (g.Cp / BK);
+    p->pair = use_pair(p->BN, p->mtiles, ceil_div(N, p->BN));
     if ((rc = encode_nhwc(&p->tmA, A, g, p->TW, p->TH))) return rc;
-    if ((rc = encode_2d(&p->tmB, Bw, N, p->K, p->K, p->BN))) return rc;
-    p->grid = dim3(ceil_div(N, p->BN), g.B * p->tiles_x * p->tiles_y);
+    if ((rc = encode_2d(&p->tmB, Bw, N, p->K, p->K, p->pair ? p->BN / 2 : p->BN))) return rc;
+    p->grid = p->pair ? dim3((p->mtiles + 1) / 2 * 2, ceil_div(N, p->BN)) : dim3(ceil_div(N, p->BN), p->mtiles);
     finish_plan(p);
     return D2S_OK;
 }
@@ -505,22 +549,32 @@ int gemm_launch(const GemmPlan *p, cudaStream_t stream) {
     a.tmA = p->tmA; a.tmB = p->tmB;
     a.M = p->M; a.N = p->N; a.kblocks = p->kblocks; a.stages = p->stages;
     a.conv = p->conv; a.H = p->H; a.W = p->W; a.Cp = p->Cp; a.TW = p->TW; a.TW_shift = p->TW == 8 ? 3 : 4;
-    a.tiles_x = p->tiles_x; a.tiles_y = p->tiles_y;
+    a.tiles_x = p->tiles_x; a.tiles_y = p->tiles_y; a.mtiles = p->mtiles;
     a.trace = p->trace;
     a.splits = p->splits; a.kb_per_split = p->kb_per_split;
     a.epi = p->epi;
     const int mode = epi_mode(p->epi);
     GemmKernel fn = nullptr;
     for (int i = 0; i < kNumVariants; ++i)
-        if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode) fn = kVariants[i].fn;
+        if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode && kVariants[i].pair == p->pair) fn = kVariants[i].fn;
     if (!fn) return set_error(D2S_ERR_UNSUPPORTED, "gemm: no kernel variant for BN=%d act=%d mode=%d", p->BN, p->epi.act, mode);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = p->grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = p->smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K: the CTAs of one output tile are one cluster
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p->splits;
-    cfg.attrs = attr; cfg.numAttrs = p->splits > 1 ? 1 : 0;
-    D2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    attr[0].val.clusterDim.x = p->pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p->splits;   // (a pair never splits K)
+    cfg.attrs = attr; cfg.numAttrs = (p->splits > 1 || p->pair) ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fn, a);
+    if (le != cudaSuccess) {
+        int nc = -1;
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&nc, fn, &cfg);
+        cudaFuncAttributes fa = {};
+        cudaFuncGetAttributes(&fa, (const void *)fn);
+        cudaGetLastError();
+        return set_error(D2S_ERR_CUDA, "gemm launch failed: %s (grid %u,%u,%u cluster %u,%u,%u smem %zu BN %d pair %d regs %d static smem %zu; occupancy query: %s, %d clusters)",
+                         cudaGetErrorString(le), p->grid.x, p->grid.y, p->grid.z, attr[0].val.clusterDim.x, attr[0].val.clusterDim.y, attr[0].val.clusterDim.z,
+                         p->smem, p->BN, p->pair, fa.numRegs, fa.sharedSizeBytes, cudaGetErrorString(oe), nc);
+    }
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return D2S_OK;
 }

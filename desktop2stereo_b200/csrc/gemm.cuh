@@ -38,7 +38,9 @@ struct ConvGeom {  // NHWC activation [B, H, W, Cp] for the implicit-GEMM A oper
 struct GemmPlan {  // everything a launch needs; built once per shape, replayed every frame
     CUtensorMap tmA, tmB;
     int M, N, K;          // conv: M = B*tiles*128 (padded), K = 9*Cp
-    int BN;               // 32 / 64 / 128
+    int BN;               // 32 / 64 / 128 / 256
+    int pair;             // 1: cta_group::2 pairs along M (256 x BN tiles)
+    int mtiles;           // real number of 128-row M tiles (the grid of a pair plan is padded to an even count)
     int stages;
     int conv;             // 0 linear, 1 implicit 3x3
     int H, W, Cp, TH, TW, tiles_x, tiles_y, B;
