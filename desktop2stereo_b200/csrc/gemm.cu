@@ -21,7 +21,7 @@ constexpr int kGemmThreads = 192;
 struct GemmArgs {
     CUtensorMap tmA, tmB;
     int M, N, kblocks, stages;
-    int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y, mtiles;
+    int conv, H, W, Cp, TW, TW_shift, tiles_x, tiles_y, mtiles, ntiles;
     int splits, kb_per_split;   // split-K: blockIdx.z owns k-blocks [z*kb_per_split, ...)
     long long *trace;           // optional: clock64 stamps of CTA (0,0,0) phases (debug)
     GemmEpi epi;
@@ -353,6 +353,202 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant for problems with more tiles than CTA slots: one CTA (or cta_group::2 pair) per SM loops over output
+// tiles; the operand ring keeps streaming across tile boundaries and the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN
+// columns), so the epilogue of tile i (TMEM -> registers -> fused epilogue -> global) overlaps the main loop of tile i+1.
+//   smem full/empty[stages]   TMA  <-> MMA
+//   tmem_full/tmem_empty[2]   MMA  <-> epilogue warps   (pair: the peer's epilogue warps arrive on the leader's tmem_empty)
+// Tiles are walked M-fastest, so the CTAs running at the same time share one B (weight) tile in L2.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int ACT, int MODE, int PAIR>
+__global__ void __launch_bounds__(kGemmThreads) gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int kBRows = PAIR ? BN / 2 : BN;
+    constexpr int kBBytes = kBRows * BK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stages = g.stages;
+    uint64_t *full = (uint64_t *)(smem + (size_t)stages * kStageBytes);
+    uint64_t *empty = full + stages;
+    uint64_t *tmem_full = empty + stages;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;      // [2]
+    uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
+    float *s_bias = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&g.tmA);
+        ptx::prefetch_tensormap(&g.tmB);
+        for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], PAIR ? 256 : 128); }
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
+    if (warp == 1) {
+        if (PAIR) { ptx::tmem_alloc_2sm(tmem_slot, 2 * BN); ptx::tmem_relinquish_2sm(); }
+        else { ptx::tmem_alloc(tmem_slot, 2 * BN); ptx::tmem_relinquish(); }
+    }
+    ptx::tc_fence_before();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+
+    // tile walk: unit = one CTA tile, or one pair tile (two M tiles); M-fastest
+    const int units_m = PAIR ? (g.mtiles + 1) / 2 : g.mtiles;
+    const int n_units = units_m * g.ntiles;
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int nkb = g.kblocks;
+    const int cchunks = g.conv ? (g.Cp / BK) : 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0; long long issued = 0;
+            uint8_t *a = smem;
+            for (int u = unit0; u < n_units; u += unit_step) {
+                const int tile_n = u / units_m, tile_m = (u - tile_n * units_m) * (PAIR ? 2 : 1) + (int)rank;
+                int img = 0, y0 = 0, x0 = 0;
+                if (g.conv) {
+                    int per_img = g.tiles_x * g.tiles_y;
+                    img = tile_m / per_img;
+                    int t = tile_m - img * per_img;
+                    y0 = (t / g.tiles_x) * (BM >> g.TW_shift);
+                    x0 = (t % g.tiles_x) * g.TW;
+                }
+                int tap = 0, cc = 0;
+                for (int i = 0; i < nkb; ++i, ++issued) {
+                    if (issued >= stages) ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (PAIR) {
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kStageBytes);
+                        if (g.conv) {
+                            int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                            ptx::tma_load_4d_2sm(a, &g.tmA, &full[s], cc * BK, x0 + dx, y0 + dy, img);
+                            if (++cc == cchunks) { cc = 0; ++tap; }
+                        } else {
+                            ptx::tma_load_2d_2sm(a, &g.tmA, &full[s], i * BK, tile_m * BM);
+                        }
+                        ptx::tma_load_2d_2sm(a + kABytes, &g.tmB, &full[s], i * BK, tile_n * BN + (int)rank * kBRows);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+                        if (g.conv) {
+                            int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                            ptx::tma_load_4d(a, &g.tmA, &full[s], cc * BK, x0 + dx, y0 + dy, img);
+                            if (++cc == cchunks) { cc = 0; ++tap; }
+                        } else {
+                            ptx::tma_load_2d(a, &g.tmA, &full[s], i * BK, tile_m * BM);
+                        }
+                        ptx::tma_load_2d(a + kABytes, &g.tmB, &full[s], i * BK, tile_n * BN);
+                    }
+                    a += kStageBytes;
+                    if (++s == stages) { s = 0; ph ^= 1; a = smem; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BN, 0);
+            int s = 0; uint32_t ph = 0;
+            uint32_t a_addr = ptx::smem_u32(smem);
+            int it = 0;
+            for (int u = unit0; u < n_units; u += unit_step, ++it) {
+                const int acc = it & 1;
+                if (it >= 2) {                                        // the epilogue must have drained this accumulator (tile it-2)
+                    ptx::mbar_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) - 1) & 1));
+                    ptx::tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int i = 0; i < nkb; ++i) {
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr);
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if (PAIR) ptx::umma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                        else ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                    }
+                    if (PAIR) ptx::umma_commit_2sm(&empty[s], 3); else ptx::umma_commit(&empty[s]);
+                    a_addr += kStageBytes;
+                    if (++s == stages) { s = 0; ph ^= 1; a_addr = ptx::smem_u32(smem); }
+                }
+                if (PAIR) ptx::umma_commit_2sm(&tmem_full[acc], 3); else ptx::umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const GemmEpi &e = g.epi;
+        const int q = warp & 3, r = q * 32 + lane;
+        const bool has_res = MODE == MODE_C16 && (e.res1 || e.res2);
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+        int it = 0;
+        for (int u = unit0; u < n_units; u += unit_step, ++it) {
+            const int acc = it & 1;
+            const int tile_n = u / units_m, tile_m = (u - tile_n * units_m) * (PAIR ? 2 : 1) + (int)rank;
+            long long orow;
+            if (g.conv) {
+                int per_img = g.tiles_x * g.tiles_y;
+                int img = tile_m / per_img;
+                int t = tile_m - img * per_img;
+                int y = (t / g.tiles_x) * (BM >> g.TW_shift) + (r >> g.TW_shift), x = (t % g.tiles_x) * g.TW + (r & (g.TW - 1));
+                orow = (y < g.H && x < g.W && tile_m < g.mtiles) ? ((long long)img * g.H + y) * g.W + x : -1;
+            } else {
+                int m = tile_m * BM + r;
+                orow = m < g.M ? m : -1;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone is done with the previous tile's bias
+            for (int t = threadIdx.x - 64; t < BN; t += 128) {
+                const int n = tile_n * BN + t;
+                s_bias[t] = (e.bias && n < g.N) ? __ldg(e.bias + n) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            ptx::mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+            ptx::tc_fence_after();
+            float head_acc = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), raw);
+                const int n0 = tile_n * BN + c * 32;
+                const bool live = orow >= 0 && n0 < g.N;
+                const long long off0 = orow * e.ldc + n0;
+                uint4 r1[4] = {z4, z4, z4, z4}, r2[4] = {z4, z4, z4, z4};
+                if (has_res && live) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n0 + j * 8 < g.N) {
+                            if (e.res1) r1[j] = __ldg((const uint4 *)(e.res1 + off0 + j * 8));
+                            if (e.res2) r2[j] = __ldg((const uint4 *)(e.res2 + off0 + j * 8));
+                        }
+                }
+                ptx::tmem_ld_wait();
+                if (c == BN / 32 - 1) {                                // the accumulator is in registers: hand the TMEM buffer back
+                    ptx::tc_fence_before();
+                    if (PAIR) ptx::mbar_arrive_leader(&tmem_empty[acc]); else ptx::mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!live) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (n0 + j * 8 >= g.N) break;
+                    float v[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(raw[j * 8 + t]);
+                    epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, 2 * BN); else ptx::tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -362,10 +558,14 @@ static EncodeTiledFn g_encode = nullptr;
 
 // the instantiations the network needs: (BN, activation, epilogue mode)
 typedef void (*GemmKernel)(const GemmArgs);
-struct Variant { int bn, act, mode, pair; GemmKernel fn; };
-#define D2S_V(bn, act, mode) {bn, act, mode, 0, gemm_tc_kernel<bn, act, mode, 0>}
-#define D2S_P(bn, act, mode) {bn, act, mode, 1, gemm_tc_kernel<bn, act, mode, 1>}
+struct Variant { int bn, act, mode, pair, persist; GemmKernel fn; };
+#define D2S_V(bn, act, mode) {bn, act, mode, 0, 0, gemm_tc_kernel<bn, act, mode, 0>}
+#define D2S_P(bn, act, mode) {bn, act, mode, 1, 0, gemm_tc_kernel<bn, act, mode, 1>}
+#define D2S_S(bn, act, mode, pair) {bn, act, mode, pair, 1, gemm_tc_persistent_kernel<bn, act, mode, pair>}
 static const Variant kVariants[] = {
+    D2S_S(256, ACT_NONE, MODE_C16, 0), D2S_S(256, ACT_RELU, MODE_C16, 0), D2S_S(256, ACT_GELU, MODE_C16, 0), D2S_S(256, ACT_NONE, MODE_X32, 0),
+    D2S_S(256, ACT_NONE, MODE_C16, 1), D2S_S(256, ACT_RELU, MODE_C16, 1), D2S_S(256, ACT_GELU, MODE_C16, 1), D2S_S(256, ACT_NONE, MODE_X32, 1),
+
     D2S_P(256, ACT_NONE, MODE_C16), D2S_P(256, ACT_RELU, MODE_C16), D2S_P(256, ACT_GELU, MODE_C16), D2S_P(256, ACT_NONE, MODE_X32),
     D2S_V(256, ACT_NONE, MODE_C16), D2S_V(256, ACT_RELU, MODE_C16), D2S_V(256, ACT_GELU, MODE_C16), D2S_V(256, ACT_NONE, MODE_X32),
     D2S_V(128, ACT_NONE, MODE_C16), D2S_V(128, ACT_RELU, MODE_C16), D2S_V(128, ACT_GELU, MODE_C16), D2S_V(128, ACT_NONE, MODE_X32),
@@ -374,6 +574,7 @@ static const Variant kVariants[] = {
 };
 #undef D2S_V
 #undef D2S_P
+#undef D2S_S
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 static int epi_mode(const GemmEpi &e) { return e.w3 ? MODE_HEAD : (e.x32 ? MODE_X32 : MODE_C16); }
 static std::once_flag g_once;
@@ -440,13 +641,19 @@ static int pick_bn(int N, int mtiles) {
     return 128;
 }
 
-// 2-CTA pairs (cta_group::2) for the 256-wide tiles.  D2S_GEMM_PAIR = 0 never, 2 whenever BN == 256, 1 (default): only when
-// the problem is several waves deep — with one tile per CTA (no persistent scheduler yet) a pair grid quantises worse than a
-// single-CTA grid at ~2 waves (M = 6224: 0.75-0.95 vs 0.89-0.96 PFLOP/s), and wins once there are many (8192^3: 1.26 vs 1.07).
+// 2-CTA pairs (cta_group::2) for the 256-wide tiles.  D2S_GEMM_PAIR = 0 never, 2 whenever BN == 256, 1 (default): only for
+// problems that run on the persistent kernel (more than two waves of tiles), and there only if the pair grid does not quantise
+// worse: rounds = ceil(units / slots) with 148 single-CTA slots or 74 pair slots; a pair unit is two tiles in ~1.86x the time
+// (profiles/r1_gemm_microbench.txt: M = 6224, N = 4096: 1.13 vs 1.05 PFLOP/s; N = 3072, where pairs need 5 rounds instead of 4:
+// 1.00 vs 1.08; 8192^3: 1.43 vs 1.29).
 static int use_pair(int BN, int mtiles, int ntiles) {
     const int mode = env_int("D2S_GEMM_PAIR", 1);
     if (BN != 256 || mtiles < 2 || mode == 0) return 0;
-    return mode == 2 || (long long)mtiles * ntiles >= 8 * kNumSMs;
+    if (mode == 2) return 1;
+    const long long tiles = (long long)mtiles * ntiles;
+    if (tiles <= 2 * kNumSMs || !env_int("D2S_GEMM_PERSIST", 1)) return 0;
+    const long long r1 = (tiles + kNumSMs - 1) / kNumSMs, rp = ((long long)((mtiles + 1) / 2) * ntiles + kNumSMs / 2 - 1) / (kNumSMs / 2);
+    return 93 * rp <= 100 * r1;
 }
 
 // Choose the split-K factor and the ring depth.  Most of this network's GEMMs are small (M = 778 tokens, or a few
@@ -488,8 +695,23 @@ static void finish_plan(GemmPlan *p) {
     if (p->BN == 256) {   // 2 x 48 KB (3 x 32 KB for a pair): two CTAs (2 x 256 TMEM columns) per SM
         stages = env_int("D2S_GEMM_BN256_STAGES", p->pair ? 3 : 2); if (stages < 2) stages = 2; if (stages > 6) stages = 6;
     }
+    // Persistent tile loop (one CTA or pair per SM, double-buffered TMEM accumulator) when there are more tiles than one wave of
+    // CTA slots.  D2S_GEMM_PERSIST = 0 never, 1 (default) heuristic.
+    p->persist = 0;
+    if (p->splits == 1 && p->BN == 256 && epi_mode(e) != MODE_HEAD && env_int("D2S_GEMM_PERSIST", 1)) {   // (128-wide tiles are ingest-bound: they need two CTAs per SM, not one deep ring)
+        const long long tiles = (long long)p->mtiles * ceil_div(p->N, p->BN);
+        if (tiles > 2 * kNumSMs) {
+            p->persist = 1;
+            stages = (int)((kMaxSmem - 4096 - (size_t)p->BN * 4) / stage);            // one CTA per SM: as deep a ring as fits
+            { int ms = env_int("D2S_GEMM_PERSIST_STAGES", 0); if (ms >= 2 && stages > ms) stages = ms; }
+            if (stages > 8) stages = 8;
+            const int units = p->pair ? (p->mtiles + 1) / 2 * ceil_div(p->N, p->BN) : (int)tiles;
+            const int slots = p->pair ? kNumSMs / 2 : kNumSMs;
+            p->grid = dim3((unsigned)((units < slots ? units : slots) * (p->pair ? 2 : 1)), 1, 1);
+        }
+    }
     p->stages = stages;
-    p->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 32 + (size_t)p->BN * 4 + 16 + 1024;
+    p->smem = (size_t)stages * stage + (2 * stages + 4) * 8 + 32 + (size_t)p->BN * 4 + 16 + 1024;
     if (env_int("D2S_VERBOSE", 0))
         fprintf(stderr, "[d2s gemm] %s M=%d N=%d K=%d BN=%d grid=(%d,%d,%d) kblocks=%d kb/split=%d stages=%d smem=%zu %s\n", p->conv ? "conv" : "lin ",
                 p->M, p->N, p->K, p->BN, p->grid.x, p->grid.y, p->grid.z, p->kblocks, p->kb_per_split, stages, p->smem,
@@ -549,14 +771,14 @@ int gemm_launch(const GemmPlan *p, cudaStream_t stream) {
     a.tmA = p->tmA; a.tmB = p->tmB;
     a.M = p->M; a.N = p->N; a.kblocks = p->kblocks; a.stages = p->stages;
     a.conv = p->conv; a.H = p->H; a.W = p->W; a.Cp = p->Cp; a.TW = p->TW; a.TW_shift = p->TW == 8 ? 3 : 4;
-    a.tiles_x = p->tiles_x; a.tiles_y = p->tiles_y; a.mtiles = p->mtiles;
+    a.tiles_x = p->tiles_x; a.tiles_y = p->tiles_y; a.mtiles = p->mtiles; a.ntiles = ceil_div(p->N, p->BN);
     a.trace = p->trace;
     a.splits = p->splits; a.kb_per_split = p->kb_per_split;
     a.epi = p->epi;
     const int mode = epi_mode(p->epi);
     GemmKernel fn = nullptr;
     for (int i = 0; i < kNumVariants; ++i)
-        if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode && kVariants[i].pair == p->pair) fn = kVariants[i].fn;
+        if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode && kVariants[i].pair == p->pair && kVariants[i].persist == p->persist) fn = kVariants[i].fn;
     if (!fn) return set_error(D2S_ERR_UNSUPPORTED, "gemm: no kernel variant for BN=%d act=%d mode=%d", p->BN, p->epi.act, mode);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = p->grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = p->smem; cfg.stream = stream;

@@ -40,6 +40,7 @@ struct GemmPlan {  // everything a launch needs; built once per shape, replayed 
     int M, N, K;          // conv: M = B*tiles*128 (padded), K = 9*Cp
     int BN;               // 32 / 64 / 128 / 256
     int pair;             // 1: cta_group::2 pairs along M (256 x BN tiles)
+    int persist;          // 1: persistent tile loop with a double-buffered TMEM accumulator (grid = one CTA or pair per SM)
     int mtiles;           // real number of 128-row M tiles (the grid of a pair plan is padded to an even count)
     int stages;
     int conv;             // 0 linear, 1 implicit 3x3

@@ -46,14 +46,19 @@ for (M, N, K, x32) in [(778, 2304, 768, False), (778, 3072, 768, False), (778, 7
     b = bench(M, N, K, x32, interleave=True)
     fl = 2 * M * N * K
     print(f"M={M} N={N} K={K} x32={x32}: back-to-back {a:7.1f} us ({fl / a / 1e6:7.1f} TFLOP/s)   interleaved with a 0-smem kernel {b:7.1f} us")
-# tile shape at tensor-bound sizes: 128x128 | 128x256 one CTA | 256x256 cta_group::2 pair (ring depth 2..4)
+# tile shape / scheduling at tensor-bound sizes
+CASES = (("128x128", dict(BN256=0, PAIR=0, PERSIST=0)), ("128x128 persist", dict(BN256=0, PAIR=0, PERSIST=1)),
+         ("128x256", dict(BN256=2, PAIR=0, PERSIST=0)), ("128x256 persist", dict(BN256=2, PAIR=0, PERSIST=1)),
+         ("pair256", dict(BN256=2, PAIR=2, PERSIST=0, BN256_STAGES=3)), ("pair256 persist", dict(BN256=2, PAIR=2, PERSIST=1)),
+         ("default", dict()))
 for (M, N, K, x32) in [(6224, 3072, 1024, False), (6224, 4096, 1024, False), (6224, 1024, 4096, True), (6224, 1024, 1024, True), (8192, 8192, 8192, False)]:
     fl = 2 * M * N * K
     res = []
-    for name, bn256, pair, nst in (("128x128", 0, 0, 0), ("128x256", 2, 0, 2), ("pair256/2st", 2, 1, 2), ("pair256/3st", 2, 1, 3), ("pair256/4st", 2, 1, 4), ("pair256/6st", 2, 1, 6)):
-        os.environ["D2S_GEMM_BN256"] = str(bn256)
-        os.environ["D2S_GEMM_PAIR"] = str(pair)
-        os.environ["D2S_GEMM_BN256_STAGES"] = str(nst or 2)
+    for name, env in CASES:
+        for k in ("BN256", "PAIR", "PERSIST", "BN256_STAGES"):
+            os.environ.pop("D2S_GEMM_" + k, None)
+        for k, v in env.items():
+            os.environ["D2S_GEMM_" + k] = str(v)
         a = bench(M, N, K, x32, iters=20)
         res.append(f"{name} {a:6.1f} us {fl / a / 1e6:5.0f} TF/s")
-    print(f"M={M} N={N} K={K} x32={x32}: " + " | ".join(res))
+    print(f"M={M} N={N} K={K} x32={x32}:\n    " + "\n    ".join(res))
