@@ -27,7 +27,20 @@ struct GemmArgs {
     GemmEpi epi;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 rounding of the value it feeds): one MUFU.RCP, one
+// MUFU.EX2 and six FMAs instead of erff()'s ~30 branchy instructions — the GELU epilogue of fc1 was epilogue-bound
+// (profiles/r1_launches_large4k.txt: 100 us with GELU vs 47 us without at M = 6224, N = 4096).
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    return copysignf(fmaf(-p * t, __expf(-ax * ax), 1.f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752440f)); }
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
@@ -360,8 +373,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
 //   tmem_full/tmem_empty[2]   MMA  <-> epilogue warps   (pair: the peer's epilogue warps arrive on the leader's tmem_empty)
 // Tiles are walked M-fastest, so the CTAs running at the same time share one B (weight) tile in L2.
 // ------------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, each takes half of the columns)
 template <int BN, int ACT, int MODE, int PAIR>
-__global__ void __launch_bounds__(kGemmThreads) gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(kPersistThreads) gemm_tc_persistent_kernel(const __grid_constant__ GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int kBRows = PAIR ? BN / 2 : BN;
     constexpr int kBBytes = kBRows * BK * 2;
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_persistent_kernel(const 
         ptx::prefetch_tensormap(&g.tmA);
         ptx::prefetch_tensormap(&g.tmB);
         for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], PAIR ? 256 : 128); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], PAIR ? 512 : 256); }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -480,7 +494,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_persistent_kernel(const 
     } else {
         // ===== epilogue warps =====
         const GemmEpi &e = g.epi;
-        const int q = warp & 3, r = q * 32 + lane;
+        const int q = warp & 3, r = q * 32 + lane;   // TMEM lane quarter this warp may access = warp id % 4
+        const int chalf = (warp - 2) >> 2;           // which half of the tile's columns this warp handles
+        constexpr int kChunks = BN / 64;             // 32-column chunks per warp
         const bool has_res = MODE == MODE_C16 && (e.res1 || e.res2);
         const uint4 z4 = make_uint4(0, 0, 0, 0);
         int it = 0;
@@ -498,17 +514,17 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_persistent_kernel(const 
                 int m = tile_m * BM + r;
                 orow = m < g.M ? m : -1;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone is done with the previous tile's bias
-            for (int t = threadIdx.x - 64; t < BN; t += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone is done with the previous tile's bias
+            for (int t = threadIdx.x - 64; t < BN; t += 256) {
                 const int n = tile_n * BN + t;
                 s_bias[t] = (e.bias && n < g.N) ? __ldg(e.bias + n) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             ptx::mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
             ptx::tc_fence_after();
             float head_acc = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf * kChunks; c < (chalf + 1) * kChunks; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), raw);
                 const int n0 = tile_n * BN + c * 32;
@@ -524,7 +540,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_persistent_kernel(const 
                         }
                 }
                 ptx::tmem_ld_wait();
-                if (c == BN / 32 - 1) {                                // the accumulator is in registers: hand the TMEM buffer back
+                if (c == (chalf + 1) * kChunks - 1) {                  // this warp's share of the accumulator is in registers: hand it back
                     ptx::tc_fence_before();
                     if (PAIR) ptx::mbar_arrive_leader(&tmem_empty[acc]); else ptx::mbar_arrive(&tmem_empty[acc]);
                 }
@@ -713,9 +729,8 @@ static void finish_plan(GemmPlan *p) {
     p->stages = stages;
     p->smem = (size_t)stages * stage + (2 * stages + 4) * 8 + 32 + (size_t)p->BN * 4 + 16 + 1024;
     if (env_int("D2S_VERBOSE", 0))
-        fprintf(stderr, "[d2s gemm] %s M=%d N=%d K=%d BN=%d grid=(%d,%d,%d) kblocks=%d kb/split=%d stages=%d smem=%zu %s\n", p->conv ? "conv" : "lin ",
-                p->M, p->N, p->K, p->BN, p->grid.x, p->grid.y, p->grid.z, p->kblocks, p->kb_per_split, stages, p->smem,
-                p->splits > 1 ? "split-K" : "");
+        fprintf(stderr, "[d2s gemm] %s M=%d N=%d K=%d BN=%d pair=%d persist=%d grid=(%u,%u,%u) kblocks=%d splits=%d stages=%d smem=%zu act=%d mode=%d\n", p->conv ? "conv" : "lin ",
+                p->M, p->N, p->K, p->BN, p->pair, p->persist, p->grid.x, p->grid.y, p->grid.z, p->kblocks, p->splits, p->stages, p->smem, e.act, epi_mode(e));
 }
 
 static int check_epi(const GemmEpi &e, int N) {
@@ -781,7 +796,7 @@ int gemm_launch(const GemmPlan *p, cudaStream_t stream) {
         if (kVariants[i].bn == p->BN && kVariants[i].act == p->epi.act && kVariants[i].mode == mode && kVariants[i].pair == p->pair && kVariants[i].persist == p->persist) fn = kVariants[i].fn;
     if (!fn) return set_error(D2S_ERR_UNSUPPORTED, "gemm: no kernel variant for BN=%d act=%d mode=%d", p->BN, p->epi.act, mode);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = p->grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = p->smem; cfg.stream = stream;
+    cfg.gridDim = p->grid; cfg.blockDim = dim3(p->persist ? kPersistThreads : kGemmThreads); cfg.dynamicSmemBytes = p->smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K: the CTAs of one output tile are one cluster
     attr[0].val.clusterDim.x = p->pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p->splits;   // (a pair never splits K)
