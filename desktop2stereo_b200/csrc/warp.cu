@@ -325,35 +325,22 @@ template <typename DT> struct StageVec<__nv_bfloat16, DT> {
 // NP consecutive depth values with one vector load (pointer aligned to NP * sizeof(DT))
 template <typename DT, int NP> struct alignas(sizeof(DT) * NP <= 16 ? sizeof(DT) * NP : 16) DepthPack { DT v[NP]; };
 
-// One warped eye pixel from the staged rows.  Same arithmetic and FMA order as eye_pixel(); the east taps are taken
-// unconditionally: when ix0 + 1 == w their weights are exactly 0 (ix == ix0 after the clip) and fma(v, 0, acc) == acc.
+// One warped eye pixel straight from global memory: the rare cases the staged window cannot serve (a tap outside the window =
+// depth outside [0,1], or a coordinate that needs grid_sample's reflection).  Same arithmetic as eye_pixel().
 template <typename RT, typename DT>
-__device__ __forceinline__ float3 eye_from_smem(const WarpK &k, const RowCtx &row, bool two, const float *s0, const float *s1, int pitch,
-                                                int lo, int tw, float gx) {
-    const float ix = source_index(gx, k.w);
-    const int ix0 = __float2int_rz(ix);   // ix >= 0 after the clip: truncation == floor
-    const float fx0 = (float)ix0;
-    const float wx0 = __fsub_rn(__fadd_rn(fx0, 1.f), ix), wx1 = __fsub_rn(ix, fx0);   // (float)(ix0 + 1) == fx0 + 1 exactly (ix0 < 2^24)
-    const float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
-    const float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
-    const int a = ix0 - lo;
-    const int b = a + (ix0 + 1 < k.w ? 1 : 0);
-    if (a < 0 || b >= tw) return taps_global<RT, DT>((const RT *)k.rgb, k.rsc, k.rsy, k.rsx, k.w, k.rgb_round, row.iy0, two, ix0, nw, ne, sw, se);   // depth outside [0,1]: left the window
-    float o[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        float acc = __fmaf_rn(s0[ch * pitch + a], nw, 0.f);
-        acc = __fmaf_rn(s0[ch * pitch + b], ne, acc);
-        if (two) {
-            acc = __fmaf_rn(s1[ch * pitch + a], sw, acc);
-            acc = __fmaf_rn(s1[ch * pitch + b], se, acc);
-        }
-        o[ch] = acc;
-    }
-    return make_float3(o[0], o[1], o[2]);
+__device__ __noinline__ float3 slow_eye(const RT *rgb, long long rsc, long long rsy, long long rsx, int w, int rgb_round, int iy0, float wy0, float wy1,
+                                        bool two, float gx) {
+    const float ix = source_index(gx, w);
+    const int ix0 = (int)floorf(ix);
+    const float wx0 = __fsub_rn((float)(ix0 + 1), ix), wx1 = __fsub_rn(ix, (float)ix0);
+    return taps_global<RT, DT>(rgb, rsc, rsy, rsx, w, rgb_round, iy0, two, ix0, __fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1),
+                               __fmul_rn(wx1, wy1));
 }
 
 __device__ __forceinline__ float clamp255(float v) { return fminf(fmaxf(v, 0.f), 255.f); }
+// staged pixel p lives at float4 index p + p/8: one pad slot per 8 pixels keeps both the 8-pixels-per-thread staging stores and
+// the strided tap loads free of shared-memory bank conflicts
+__device__ __forceinline__ int px_slot(int p) { return p + (p >> 3); }
 
 // OL: output layout known at compile time — 0: HWC contiguous (sx = 3, sc = 1), 1: planar CHW (sx = 1)
 // flags: bit 0 = rgb rows may be staged with 16-byte loads, bit 1 = depth rows may be read with vector loads
@@ -362,43 +349,58 @@ __global__ void __launch_bounds__(THREADS) warp_sbs_fast_kernel(const WarpK k, i
     typedef typename Vec4<OT>::type V;
     constexpr int NP = HALF ? 8 : 4;                 // source pixels per thread (4 output pixels per eye)
     constexpr int SEG = THREADS * NP;                // source pixels per block
-    extern __shared__ __align__(16) float s_rgb[];   // [rows(1|2)][3][pitch]
+    extern __shared__ __align__(16) float4 s_px[];   // [rows(1|2)][pitch4]: staged pixels, (r, g, b, -) as fp32
     const int y = blockIdx.y;
     const int seg0 = blockIdx.x * SEG;
-    const int pitch = SEG + 2 * margin;              // margin is a multiple of 8 => lo, pitch are too
-    const int lo = max(seg0 - margin, 0), hi = min(seg0 + SEG + margin, k.w);   // staged source columns [lo, hi)
+    const int pitch4 = px_slot(SEG + 2 * margin) + 1;
+    const int lo = max(seg0 - margin, 0), hi = min(seg0 + SEG + margin, k.w);   // staged source columns [lo, hi); margin % 16 == 0
     const int tw = hi - lo;
     const RowCtx row = make_row(k, y);
     const bool two = row.ok1 && row.wy1 != 0.f;      // second source row contributes (block-uniform)
     const int nrows = two ? 2 : 1;
+    // the depth values of this thread's pixels: issued first, so that their DRAM round trip overlaps the staging loads
+    const int x0 = seg0 + threadIdx.x * NP;
+    const int npx = min(NP, k.w - x0);               // <= 0: thread beyond the row; < NP only for the last thread of a row
+    DepthPack<DT, NP> pk;
+    const bool dvec = (flags & 2) && npx == NP;
+    if (dvec) pk = *(const DepthPack<DT, NP> *)((const DT *)k.depth + (size_t)y * k.w + x0);
     {
         typedef StageVec<RT, DT> SV;
         const bool rr = k.rgb_round;
         const int nv = (flags & 1) ? tw / SV::N : 0;
-        for (int r = 0; r < nrows; ++r)
+        const RT *src = (const RT *)k.rgb + (long long)row.iy0 * k.rsy + (long long)lo * k.rsx;
+        for (int i = threadIdx.x; i < nv; i += THREADS) {
+            uint4 raw[2][3];                         // every load of both rows in flight before the first use
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float *dst = s_rgb + (r * 3 + c) * pitch;
-                const RT *src = (const RT *)k.rgb + c * k.rsc + (long long)(row.iy0 + r) * k.rsy + (long long)lo * k.rsx;
-                for (int i = threadIdx.x; i < nv; i += THREADS) {
-                    float f[SV::N];
-                    SV::unpack(__ldg((const uint4 *)src + i), rr, f);
-#pragma unroll
-                    for (int j = 0; j < SV::N; j += 4) *(float4 *)(dst + i * SV::N + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                }
-                for (int x = nv * SV::N + threadIdx.x; x < tw; x += THREADS)
-                    dst[x] = stage_value<RT, DT>(to_f32<RT>(__ldg(src + (long long)x * k.rsx)), rr);
+                raw[0][c] = __ldg((const uint4 *)(src + c * k.rsc) + i);
+                if (two) raw[1][c] = __ldg((const uint4 *)(src + k.rsy + c * k.rsc) + i);
             }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (r == 1 && !two) break;
+                float f0[SV::N], f1[SV::N], f2[SV::N];
+                SV::unpack(raw[r][0], rr, f0); SV::unpack(raw[r][1], rr, f1); SV::unpack(raw[r][2], rr, f2);
+                float4 *dst = s_px + r * pitch4;
+#pragma unroll
+                for (int j = 0; j < SV::N; ++j) dst[px_slot(i * SV::N + j)] = make_float4(f0[j], f1[j], f2[j], 0.f);
+            }
+        }
+        for (int r = 0; r < nrows; ++r) {
+            float4 *dst = s_px + r * pitch4;
+            for (int x = nv * SV::N + threadIdx.x; x < tw; x += THREADS) {
+                const RT *p = src + r * k.rsy + (long long)x * k.rsx;
+                dst[px_slot(x)] = make_float4(stage_value<RT, DT>(to_f32<RT>(__ldg(p)), rr), stage_value<RT, DT>(to_f32<RT>(__ldg(p + k.rsc)), rr),
+                                              stage_value<RT, DT>(to_f32<RT>(__ldg(p + 2 * k.rsc)), rr), 0.f);
+            }
+        }
     }
     __syncthreads();
-    const int x0 = seg0 + threadIdx.x * NP;
     if (x0 >= k.w) return;
-    const float *s0 = s_rgb, *s1 = s_rgb + 3 * pitch;
-    const int npx = min(NP, k.w - x0);               // < NP only for the last thread of a row
+    const float4 *s0 = s_px, *s1 = s_px + pitch4;
 
     float dv[NP];
-    if ((flags & 2) && npx == NP) {
-        const DepthPack<DT, NP> pk = *(const DepthPack<DT, NP> *)((const DT *)k.depth + (size_t)y * k.w + x0);
+    if (dvec) {
 #pragma unroll
         for (int p = 0; p < NP; ++p) dv[p] = to_f32<DT>(pk.v[p]);
     } else {
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(THREADS) warp_sbs_fast_kernel(const WarpK k, i
         for (int p = 0; p < NP; ++p) dv[p] = load_depth<DT>(k, y, min(x0 + p, k.w - 1));   // clamped duplicates are never stored
     }
 
+    const float span = (float)(k.w - 1);
     float v[2][4][3];                                // [eye][output pixel][channel]
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -419,7 +422,31 @@ __global__ void __launch_bounds__(THREADS) warp_sbs_fast_kernel(const WarpK k, i
         const float xs = linspace_pm1(x, k.w, k.xstep, k.xhalf);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const float3 c = eye_from_smem<RT, DT>(k, row, two, s0, s1, pitch, lo, tw, e ? __fsub_rn(xs, sn) : __fadd_rn(xs, sn));
+            // grid_sampler source index (same operations as source_index(); the reflection case is left to slow_eye)
+            const float gx = e ? __fsub_rn(xs, sn) : __fadd_rn(xs, sn);
+            const float in = fabsf(__fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), span));
+            const float ix = fminf(span, fmaxf(in, 0.f));
+            const int ix0 = __float2int_rz(ix);      // ix >= 0 after the clip: truncation == floor
+            const float fx0 = (float)ix0;
+            const float wx0 = __fsub_rn(__fadd_rn(fx0, 1.f), ix), wx1 = __fsub_rn(ix, fx0);   // (float)(ix0 + 1) == fx0 + 1 exactly (ix0 < 2^24)
+            const int a = ix0 - lo, b = a + (ix0 + 1 < k.w ? 1 : 0);
+            // the east taps are taken unconditionally: when ix0 + 1 == w their weights are exactly 0 (ix == ix0 after the clip)
+            const int ia = px_slot(min(max(a, 0), tw - 1)), ib = px_slot(min(max(b, 0), tw - 1));
+            const float4 p00 = s0[ia], p01 = s0[ib];
+            const float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
+            float3 c;
+            c.x = __fmaf_rn(p01.x, ne, __fmaf_rn(p00.x, nw, 0.f));
+            c.y = __fmaf_rn(p01.y, ne, __fmaf_rn(p00.y, nw, 0.f));
+            c.z = __fmaf_rn(p01.z, ne, __fmaf_rn(p00.z, nw, 0.f));
+            if (two) {
+                const float4 p10 = s1[ia], p11 = s1[ib];
+                const float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
+                c.x = __fmaf_rn(p11.x, se, __fmaf_rn(p10.x, sw, c.x));
+                c.y = __fmaf_rn(p11.y, se, __fmaf_rn(p10.y, sw, c.y));
+                c.z = __fmaf_rn(p11.z, se, __fmaf_rn(p10.z, sw, c.z));
+            }
+            if (in >= span || a < 0 || b >= tw)      // rare: outside the staged window, or a coordinate grid_sample would reflect
+                c = slow_eye<RT, DT>((const RT *)k.rgb, k.rsc, k.rsy, k.rsx, k.w, k.rgb_round, row.iy0, row.wy0, row.wy1, two, gx);
             if (!HALF) {
                 v[e][p & 3][0] = clamp255(c.x); v[e][p & 3][1] = clamp255(c.y); v[e][p & 3][2] = clamp255(c.z);   // final clamp, depth.py:2184
             } else if ((p & 1) == 0) {
@@ -490,10 +517,11 @@ static int launch_depth(const WarpK &k, int depth_dtype, int out_dtype, dim3 gri
 
 template <typename RT, typename DT, typename OT>
 static int launch_fast_t(const WarpK &k, bool half, int margin, d2s_stream_t st) {
-    constexpr int kFull = 256, kHalf = 128;          // threads per block: 1024 source pixels per block either way
-    const int seg = 1024;
+    constexpr int kFull = 128, kHalf = 128;          // threads per block: 512 (Full) / 1024 (Half-SBS) source pixels per block
+    const int seg = half ? 1024 : 512;               // small blocks: while some blocks of an SM wait on their staging loads, others compute
     dim3 grid(ceil_div(k.w, seg), k.h);
-    size_t smem = (size_t)2 * 3 * (seg + 2 * margin) * sizeof(float);
+    const int padded = seg + 2 * margin;
+    size_t smem = (size_t)2 * (padded + (padded >> 3) + 1) * sizeof(float4);
     const bool hwc = k.osx == 3 && k.osc == 1, chw = k.osx == 1;
     if (!hwc && !chw) return -1;
     int flags = 0;
