@@ -98,7 +98,7 @@ class ClockSampler:
 
 
 def build_hf_model(variant=VARIANT, seed=SEED):
-    from oracle.ref_harness import make_hf_model   # seeded random-init weights (no checkpoints offline)
+    from desktop2stereo_b200.synth import make_hf_model   # seeded random-init weights (no checkpoints offline)
     return make_hf_model(variant, seed)
 
 
@@ -144,6 +144,7 @@ WORKLOADS = {
     # name: (variant, frame h, frame w, frames per engine call, description)
     "base1080": ("Base", 1080, 1920, 1, "BASELINE.json configs[1]: DA-V2-Base, 1080p BGRA batch=1 -> Full-SBS (model input 294x518, 778 tokens)"),
     "large4k": ("Large", 2160, 3840, 8, "BASELINE.json configs[2]: DA-V2-Large, 4K BGRA batch=8 -> Full-SBS (model input 8 x 294x518, 6224 token rows)"),
+    "vda1080": ("vits", 1080, 1920, 1, "BASELINE.json configs[3]: streaming Video-Depth-Anything, 1080p, 32-frame temporal window, one video per CUDA stream"),
 }
 
 
@@ -156,6 +157,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--slots", type=int, default=8, help="frames in flight (CUDA streams) in the pipelined legs")
+    ap.add_argument("--vda-encoder", default="vits", choices=["vits", "vitb", "vitl"])
     ap.add_argument("--workload", default="base1080", choices=sorted(WORKLOADS),
                     help="base1080 is the headline (configs[1]); large4k (configs[2]) is an extra measurement, not the default line")
     args = ap.parse_args()
@@ -163,6 +165,8 @@ def main():
         return run_reference(args)
     if args.workload == "large4k":
         return run_large4k(args)
+    if args.workload == "vda1080":
+        return run_vda1080(args)
 
     import numpy as np
     import torch
@@ -442,6 +446,78 @@ def run_large4k(args):
                          "traffic": None, "peak_source": src, "gflop_per_launch": gflop, "duration_ms": float(st[1])},
             "roofline_warp": {"kernel": "warp_sbs_fast_kernel x8 (+ postprocess x8)", "bound": "hbm", "bytes_per_launch": h * w * 32,
                               "note": "stage time covers 8 post-process chains and 8 warp launches"}}
+    print(json.dumps(line))
+    return 0
+
+
+def run_vda1080(args):
+    """configs[3]: streaming Video-Depth-Anything at 1080p.  The temporal state makes consecutive frames of ONE video sequential,
+    so the unit of parallelism is the video: `--slots` videos run on `--slots` CUDA streams of one GPU (one per GPU across GPUs:
+    "replicas only").  One step = one frame of every video; value = frames/s over all videos.  Extra measurement."""
+    import numpy as np
+    import torch
+    from desktop2stereo_b200 import _lib
+    from desktop2stereo_b200.engine import B200Engine
+    from desktop2stereo_b200.prepost import PostProcessor, preprocess, process
+    from desktop2stereo_b200.stereo import make_sbs_core
+    from desktop2stereo_b200.synth import make_vda_state_dict
+    h, w, S = 1080, 1920, args.slots
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    engine = B200Engine.from_vda_state_dict(make_vda_state_dict(args.vda_encoder, SEED), args.vda_encoder, dev, out_dtype=torch.float16)
+    g = torch.Generator(device=dev).manual_seed(SEED)
+    RING = 24
+    frames = [torch.randint(0, 256, (h, w, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(RING)]
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    posts = [PostProcessor() for _ in range(S)]
+    outs = [torch.empty((h, 2 * w, 3), dtype=torch.float32, device=dev) for _ in range(S)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(i):
+        for s_, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                rgb = process(frames[(i * S + s_) % RING], h)
+                x = preprocess(rgb, 518, 14)
+                raw = engine(x)
+                d = posts[s_](raw.reshape(raw.shape[-2:]), out_size=(h, w))
+                make_sbs_core(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC", out=outs[s_])
+
+    warmup = max(args.warmup, 3)
+    for i in range(warmup + 33):            # past the 32-frame window: steady state
+        step(i)
+    torch.cuda.synchronize()
+    # one video alone (latency view)
+    s0, e0 = ev(), ev()
+    with torch.cuda.stream(streams[0]):
+        s0.record()
+        for i in range(20):
+            rgb = process(frames[i % RING], h); x = preprocess(rgb, 518, 14); raw = engine(x)
+            d = posts[0](raw.reshape(raw.shape[-2:]), out_size=(h, w))
+            make_sbs_core(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC", out=outs[0])
+        e0.record()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dev.index or 0); clocks.start()
+    l0 = L.d2s_launch_count()
+    s, e = ev(), ev()
+    s.record()
+    for st in streams:
+        st.wait_event(s)
+    for i in range(args.steps):
+        step(i)
+    for st in streams:
+        e.wait(st) if False else torch.cuda.current_stream(dev).wait_stream(st)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    line = {"metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": S * args.steps / (ms / 1e3), "unit": "frames/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOADS["vda1080"][4] + f" ({args.vda_encoder}, model input 294x518)", "parallelism": f"{S} videos on {S} CUDA streams",
+                       "l2": f"ring of {RING} distinct frames (199 MB) > 126 MB L2"},
+            "gpu_launches": int(L.d2s_launch_count() - l0), "clocks": clocks.stop(),
+            "single_video": {"ms_per_frame": s0.elapsed_time(e0) / 20, "fps": 20 / (s0.elapsed_time(e0) / 1e3)},
+            "state_bytes_per_video": None}
     print(json.dumps(line))
     return 0
 

@@ -21,67 +21,7 @@ import tempfile
 
 REFERENCE_ROOT = os.environ.get("D2S_REFERENCE_ROOT", "/root/reference")
 
-# name -> (hidden, layers, heads, out_indices, neck_hidden_sizes, fusion_hidden_size)
-# depth.py:889-893 (VDA table) and the HF `-hf` checkpoints' config.json.
-DA_V2_VARIANTS = {
-    "Small": (384, 12, 6, [3, 6, 9, 12], [48, 96, 192, 384], 64),
-    "Base": (768, 12, 12, [3, 6, 9, 12], [96, 192, 384, 768], 128),
-    "Large": (1024, 24, 16, [5, 12, 18, 24], [256, 512, 1024, 1024], 256),
-}
-
-
-def make_hf_model(variant: str = "Small", seed: int = 0, tiny: dict | None = None):
-    """Seeded random-init HF DepthAnythingForDepthEstimation (fp32, eval).
-
-    `tiny` overrides (hidden, layers, heads, out_indices, neck, fusion) for small golden cases.
-    Parameters that HF initialises to constants (LayerScale=1, biases=0, LN) are re-drawn so that
-    every term of the forward pass is exercised by parity tests.
-    """
-    import torch
-    from transformers import DepthAnythingConfig, DepthAnythingForDepthEstimation, Dinov2Config
-
-    hidden, layers, heads, out_idx, neck, fusion = DA_V2_VARIANTS[variant] if tiny is None else (
-        tiny["hidden"], tiny["layers"], tiny["heads"], tiny["out_indices"], tiny["neck"], tiny["fusion"])
-    bcfg = Dinov2Config(
-        hidden_size=hidden, num_hidden_layers=layers, num_attention_heads=heads,
-        image_size=518, patch_size=14, out_indices=out_idx,
-        apply_layernorm=True, reshape_hidden_states=False,
-    )
-    cfg = DepthAnythingConfig(
-        backbone_config=bcfg, reassemble_hidden_size=hidden, patch_size=14,
-        neck_hidden_sizes=neck, fusion_hidden_size=fusion, head_hidden_size=32,
-        reassemble_factors=[4, 2, 1, 0.5], head_in_index=-1,
-        depth_estimation_type="relative",
-    )
-    torch.manual_seed(seed)
-    model = DepthAnythingForDepthEstimation(cfg).eval()
-    randomize_constant_params(model, seed + 1)
-    return model
-
-
-def randomize_constant_params(model, seed: int):
-    """Give biases / LayerNorm / LayerScale non-trivial seeded values (deterministic by name order)."""
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    with torch.no_grad():
-        for name, p in sorted(model.named_parameters()):
-            if name.endswith("weight") and p.dim() >= 2:
-                # variance-preserving re-draw: HF's default trunc-normal(0.02) init makes every activation collapse
-                # towards 0 and the final ReLU output identically 0, which would make parity tests vacuous
-                fan_in = p[0].numel() if "resize" not in name or p.dim() != 4 or "layers.3" in name else p.shape[0] * p[0, 0].numel()
-                p.copy_(torch.randn(p.shape, generator=g) * (1.0 / fan_in ** 0.5))
-                continue
-            if name == "head.conv3.bias":
-                p.fill_(0.5)
-                continue
-            if name.endswith("lambda1"):
-                p.copy_(0.5 + torch.rand(p.shape, generator=g))
-            elif "norm" in name and name.endswith("weight"):
-                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
-            elif name.endswith("bias"):
-                p.copy_(0.05 * torch.randn(p.shape, generator=g))
-            elif name.endswith("cls_token") or name.endswith("position_embeddings"):
-                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+from desktop2stereo_b200.synth import DA_V2_VARIANTS, make_hf_model, randomize_constant_params  # noqa: E402,F401  (seeded weights live with the product's bench helpers)
 
 
 def load_reference(variant: str = "Small", depth_resolution: int = 518, fp16: bool = False,
