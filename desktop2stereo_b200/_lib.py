@@ -65,6 +65,7 @@ SYMBOLS = {
     "d2s_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(ModelConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "d2s_destroy": (C.c_int, [C.c_void_p]),
     "d2s_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "d2s_set_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "d2s_reset_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "d2s_debug_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
     "d2s_workspace_bytes": (C.c_size_t, [C.c_void_p]),

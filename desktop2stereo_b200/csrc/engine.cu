@@ -88,6 +88,7 @@ struct d2s_engine {
     std::mutex mu;
     d2s::ShapePlan *last = nullptr;
     bool use_graph = true;
+    int policy = 0;                      // D2S_POLICY_LATENCY / D2S_POLICY_THROUGHPUT for the plans built next
 };
 
 namespace d2s {
@@ -524,7 +525,7 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
     cudaStream_t st = (cudaStream_t)stream;
     // One plan (activation buffers + tensor maps + graph) per shape AND per stream: frames submitted on different streams
     // run concurrently on disjoint buffers while sharing the (read-only) weights.
-    std::vector<long long> key = {B, H, W, in_dtype, out_dtype, (long long)(uintptr_t)stream};
+    std::vector<long long> key = {B, H, W, in_dtype, out_dtype, (long long)(uintptr_t)stream, h->policy};
     std::unique_lock<std::mutex> lock(h->mu);
     auto it = h->plans.find(key);
     if (it == h->plans.end()) {
@@ -532,7 +533,9 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
         // like the reference's lazy engine build at depth.py:1842-1862)
         std::unique_ptr<ShapePlan> sp(new ShapePlan());
         sp->B = B; sp->H = H; sp->W = W; sp->in_dtype = in_dtype; sp->out_dtype = out_dtype; sp->stream = st;
+        gemm_set_plan_policy(h->policy);
         int rc = build_plan(h, sp.get());
+        gemm_set_plan_policy(0);
         if (rc) return rc;
         if (h->use_graph) {
             cudaStream_t cs;
@@ -558,6 +561,13 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
         if (rc) return rc;
     }
     D2S_CHECK_CUDA(cudaMemcpyAsync(depth_out, sp->out_stage, sp->out_bytes, cudaMemcpyDeviceToDevice, st));
+    return D2S_OK;
+}
+
+extern "C" int d2s_set_policy(d2s_handle h, int policy) {
+    D2S_REQUIRE(h != nullptr && (policy == D2S_POLICY_LATENCY || policy == D2S_POLICY_THROUGHPUT), "d2s_set_policy: bad arguments");
+    std::unique_lock<std::mutex> lock(h->mu);
+    h->policy = policy;
     return D2S_OK;
 }
 

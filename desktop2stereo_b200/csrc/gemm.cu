@@ -649,10 +649,16 @@ static int env_int(const char *name, int dflt) {
 // SM when every SM streams): a 128 x 128 tile ingests 32 KB per 2.1 MFLOP k-block = 64 FLOP/B -> ~0.77 PFLOP/s chip-wide, which is
 // what the kernel measures (0.80-0.86).  A 128 x 256 tile ingests 48 KB per 4.2 MFLOP = 85 FLOP/B.  It is used when the problem has
 // enough 256-wide tiles to fill every SM (large batches; +16 % at M = 6224, profiles/r1_gemm_microbench.txt); small problems keep 128-wide tiles for parallelism (and split-K).
+// Plan policy (set by the engine around plan construction): 0 = latency (one frame alone on the GPU: many small tiles, split-K),
+// 1 = throughput (several frames in flight share the GPU: 256-wide tiles whenever N allows — fewer, fatter CTAs, 33 % less L2
+// ingest per FLOP and half the per-CTA fixed cost; measured +14 % frames/s at 8 frames in flight for +0.6 ms single-frame latency).
+static thread_local int g_plan_policy = 0;
+void gemm_set_plan_policy(int policy) { g_plan_policy = policy; }
+
 static int pick_bn(int N, int mtiles) {
     if (N <= 32) return 32;
     if (N <= 64) return 64;
-    const int mode = env_int("D2S_GEMM_BN256", 1);    // 0 never, 1 heuristic, 2 whenever N allows
+    const int mode = env_int("D2S_GEMM_BN256", g_plan_policy == 1 ? 2 : 1);    // 0 never, 1 heuristic, 2 whenever N allows
     if (mode && N % 256 == 0 && (mode == 2 || (long long)mtiles * (N / 256) >= kNumSMs)) return 256;
     return 128;
 }

@@ -58,6 +58,7 @@ int gemm_plan_linear(GemmPlan *p, const __half *A, int lda, const __half *Bw, in
 // A: NHWC fp16 [B,H,W,Cp]; Bw: [N, 9*Cp] with k = (ky*3+kx)*Cp + c.  Output rows are pixels (b,y,x) -> (b*H+y)*W+x.
 int gemm_plan_conv3x3(GemmPlan *p, const __half *A, const ConvGeom &g, const __half *Bw, int N, const GemmEpi &epi);
 int gemm_launch(const GemmPlan *p, cudaStream_t stream);
+void gemm_set_plan_policy(int policy);   // 0 latency, 1 throughput: tile-shape heuristics of the plans built next on this thread
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes (idempotent)
 
 }  // namespace d2s

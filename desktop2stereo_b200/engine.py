@@ -26,6 +26,7 @@ class B200Engine:
         if self.device.type != "cuda":
             raise _lib.D2SError("B200Engine needs a CUDA device; there is no CPU path")
         self.cfg, self.out_dtype = cfg, out_dtype
+        self.policy = "latency"
         blob = np.ascontiguousarray(blob, dtype=np.float32)
         self._h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -68,6 +69,12 @@ class B200Engine:
             _lib.check(_lib.lib().d2s_infer(self._h, tensor.data_ptr(), _TORCH2D2S[tensor.dtype], out.data_ptr(),
                                             _TORCH2D2S[odt], B, H, W, _stream_ptr(tensor.device)), "d2s_infer")
         return out.view(B, 1, H, W) if self.cfg.temporal else out     # VDA returns [T,1,H,W] (vda2_s.py:80-84)
+
+    def set_policy(self, policy: str):
+        """'latency' (default: one frame alone on the GPU) or 'throughput' (several frames in flight): tile shapes of the plans
+        built by the next calls.  StereoPipeline switches to 'throughput' when it keeps more than one frame in flight."""
+        _lib.check(_lib.lib().d2s_set_policy(self._h, {"latency": 0, "throughput": 1}[policy]), "d2s_set_policy")
+        self.policy = policy
 
     def reset(self):
         """Temporal engines: forget the state of the current stream (the next frame is a first frame, vda2_s.py:196)."""

@@ -57,7 +57,15 @@ class StereoPipeline:
         if ev: ev[0].record(s.stream)
         rgb = d2s_depth.process(frame_dev, h)
         if ev: ev[1].record(s.stream)
-        depth = d2s_depth.predict_depth(rgb, use_temporal_smooth=self.use_temporal_smooth)
+        engine = d2s_depth.model_wraper.model
+        prev = getattr(engine, "policy", None)
+        if prev is not None and len(self.slots) > 1:
+            engine.set_policy("throughput")        # several frames share the GPU: fewer, wider GEMM tiles
+        try:
+            depth = d2s_depth.predict_depth(rgb, use_temporal_smooth=self.use_temporal_smooth)
+        finally:
+            if prev is not None and len(self.slots) > 1:
+                engine.set_policy(prev)
         if ev: ev[2].record(s.stream)
         sbs = make_sbs_core(rgb, depth, out_layout="HWC", out_dtype=self.out_dtype, **self.params)
         if ev:

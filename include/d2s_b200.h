@@ -130,6 +130,11 @@ int d2s_destroy(d2s_handle h);
 /* pixel_values [B,3,H,W] (F16 or F32, normalised) -> predicted_depth [B,H,W] (F16 or F32). */
 int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, void *depth_out, int out_dtype,
               int B, int H, int W, d2s_stream_t stream);
+/* Tile-shape policy of the plans d2s_infer builds from now on (plans of both policies coexist, keyed by stream and policy):
+ * LATENCY (default): one frame alone on the GPU — many small tiles, split-K.  THROUGHPUT: several frames in flight on several
+ * streams — fewer, wider tiles.  Results agree to fp16 rounding (different accumulation splits), each policy is deterministic. */
+enum d2s_policy { D2S_POLICY_LATENCY = 0, D2S_POLICY_THROUGHPUT = 1 };
+int d2s_set_policy(d2s_handle h, int policy);
 /* temporal engines: forget the stream state (frame counter + K/V rings) of the plan(s) bound to `stream` — the next frame is a
  * first frame again (vda2_s.py:196 `if not self.transform`). */
 int d2s_reset_stream(d2s_handle h, d2s_stream_t stream);

@@ -96,3 +96,25 @@ def test_engine_rejects_bad_input(cuda_device):
     with pytest.raises(_lib.D2SError):
         eng(torch.zeros(1, 3, 70, 70))                             # CPU tensor: no CPU path
     eng.close()
+
+
+def test_engine_throughput_policy(cuda_device):
+    """The throughput policy (wide tiles, what StereoPipeline uses with several frames in flight) computes the same network:
+    within the fp16 bound of the fp32 reference, deterministic, and its plans coexist with the latency plans."""
+    from desktop2stereo_b200.engine import B200Engine
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = make_hf_model("Base", 7)
+    eng = B200Engine.from_hf_model(model, cuda_device, out_dtype=torch.float32)
+    x = torch.from_numpy(model_input(7, 1, 294, 518)).to(cuda_device)
+    lat = eng(x).clone()
+    eng.set_policy("throughput")
+    thr = eng(x).clone()
+    assert torch.equal(eng(x), thr)
+    eng.set_policy("latency")
+    assert torch.equal(eng(x), lat)
+    with torch.no_grad():
+        ref = model.to(cuda_device)(pixel_values=x).predicted_depth
+    print("latency vs ref", _rel(lat, ref), "throughput vs ref", _rel(thr, ref), "latency vs throughput", _rel(thr, lat))
+    assert _rel(lat, ref) <= 5e-3 and _rel(thr, ref) <= 5e-3
+    eng.close()
