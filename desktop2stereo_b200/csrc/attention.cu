@@ -117,15 +117,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half *__restrict
         }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float c0 = exp2f((m0 - mx0) * scale_log2e), c1 = exp2f((m1 - mx1) * scale_log2e);  // first block: exp2(-inf) = 0
+        const float c0 = fast_exp2((m0 - mx0) * scale_log2e), c1 = fast_exp2((m1 - mx1) * scale_log2e);  // first block: exp2(-inf) = 0
         m0 = mx0; m1 = mx1;
         const float ms0 = mx0 * scale_log2e, ms1 = mx1 * scale_log2e;
         float rs0 = 0.f, rs1 = 0.f;
         uint32_t pf[4][4];  // P as the A operand of P V: 4 k-steps of 16 keys
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            float p0 = exp2f(s[nt][0] * scale_log2e - ms0), p1 = exp2f(s[nt][1] * scale_log2e - ms0);
-            float p2 = exp2f(s[nt][2] * scale_log2e - ms1), p3 = exp2f(s[nt][3] * scale_log2e - ms1);
+            float p0 = fast_exp2(s[nt][0] * scale_log2e - ms0), p1 = fast_exp2(s[nt][1] * scale_log2e - ms0);
+            float p2 = fast_exp2(s[nt][2] * scale_log2e - ms1), p3 = fast_exp2(s[nt][3] * scale_log2e - ms1);
             rs0 += p0 + p1; rs1 += p2 + p3;
             pf[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(p0, p1);
             pf[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(p2, p3);

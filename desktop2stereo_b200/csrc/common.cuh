@@ -48,6 +48,13 @@ constexpr int kNumSMs = 148;  // B200
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// 2^x on the SFU (MUFU.EX2): 2 ulp, flushes denormals, exp2(-inf) = 0 — what the softmax kernels need, without exp2f()'s range fix-ups
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---- dtype load/store (device) ----
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

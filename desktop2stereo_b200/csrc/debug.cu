@@ -47,5 +47,17 @@ extern "C" int d2s_debug_conv3x3(const void *A, const void *Wt, const float *bia
 
 extern "C" int d2s_debug_attention(const void *qkv, void *out, int B, int N, int D, int heads, d2s_stream_t stream) {
     D2S_REQUIRE(qkv && out, "d2s_debug_attention: null argument");
-    return attention_launch((const __half *)qkv, (__half *)out, B, N, D, heads, (cudaStream_t)stream);
+    const char *v = getenv("D2S_ATTN");
+    if (!(v && v[0] == 't')) return attention_launch((const __half *)qkv, (__half *)out, B, N, D, heads, (cudaStream_t)stream);   // mma.sync version (default); D2S_ATTN=tcgen05 runs the tcgen05 kernel below
+    // tcgen05 version: throw-away V^T scratch (allocated, zeroed, used, synchronised, freed)
+    __half *vt = nullptr;
+    const size_t n = attention_tc_vt_elems(B, N, heads);
+    D2S_CHECK_CUDA(cudaMalloc(&vt, n * sizeof(__half)));
+    D2S_CHECK_CUDA(cudaMemsetAsync(vt, 0, n * sizeof(__half), (cudaStream_t)stream));
+    AttnTcPlan p;
+    int rc = attention_tc_plan(&p, (const __half *)qkv, vt, (__half *)out, B, N, D, heads);
+    if (rc == D2S_OK) rc = attention_tc_launch(&p, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(vt);
+    return rc;
 }

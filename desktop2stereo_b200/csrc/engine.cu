@@ -347,12 +347,23 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     for (int i = 0; i < 4; ++i) TRY(plan_alloc(sp, &feat[i], (size_t)BP * D));
     const float eps = c.layer_norm_eps;
     const int heads = c.heads, mlp = c.mlp_hidden;
+    // attention: the mma.sync flash kernel by default; D2S_ATTN=tcgen05 selects the tcgen05 kernel (attention_tc.cu: correct, but
+    // not faster yet — 24 + 10 us (V^T transpose) vs 18 us at B=1 x 6 heads, 98 + 19 vs 106 us at B=8 x 16 heads)
+    const char *attn_env = getenv("D2S_ATTN");
+    const bool attn_tc = attn_env && attn_env[0] == 't';
+    AttnTcPlan attn{};
+    if (attn_tc) {
+        __half *vt16;
+        TRY(plan_alloc(sp, &vt16, attention_tc_vt_elems(B, N, heads)));
+        TRY(attention_tc_plan(&attn, qkv16, vt16, att16, B, N, D, heads));
+    }
     for (int l = 0; l < c.layers; ++l) {
         const LayerW lw = e->layers[l];
         sp->ops.push_back([=](cudaStream_t st) { return layernorm_launch(X, lw.ln1_w, lw.ln1_b, ln16, M, D, eps, 0, N, st); });
         GemmEpi eq; eq.bias = lw.qkv_b; eq.c16 = qkv16; eq.ldc = 3 * D;
         TRY(add_linear(sp, ln16, D, lw.qkv_w, D, M, 3 * D, D, eq));
-        sp->ops.push_back([=](cudaStream_t st) { return attention_launch(qkv16, att16, B, N, D, heads, st); });
+        if (attn_tc) sp->ops.push_back([=](cudaStream_t st) { return attention_tc_launch(&attn, st); });
+        else sp->ops.push_back([=](cudaStream_t st) { return attention_launch(qkv16, att16, B, N, D, heads, st); });
         GemmEpi epj; epj.bias = lw.proj_b; epj.x32 = X; epj.ldc = D;   // LayerScale folded; X += ...
         TRY(add_linear(sp, att16, D, lw.proj_w, D, M, D, D, epj));
         sp->ops.push_back([=](cudaStream_t st) { return layernorm_launch(X, lw.ln2_w, lw.ln2_b, ln16, M, D, eps, 0, N, st); });

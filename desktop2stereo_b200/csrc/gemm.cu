@@ -615,7 +615,7 @@ int gemm_init() {
     return g_init_rc;
 }
 
-static int encode_2d(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+int tma_encode_2d(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld_elems * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
@@ -759,8 +759,8 @@ int gemm_plan_linear(GemmPlan *p, const __half *A, int lda, const __half *Bw, in
     p->kblocks = ceil_div(K, BK);
     p->mtiles = ceil_div(M, BM);
     p->pair = use_pair(p->BN, p->mtiles, ceil_div(N, p->BN));
-    if ((rc = encode_2d(&p->tmA, A, M, K, lda, BM))) return rc;
-    if ((rc = encode_2d(&p->tmB, Bw, N, K, ldb, p->pair ? p->BN / 2 : p->BN))) return rc;
+    if ((rc = tma_encode_2d(&p->tmA, A, M, K, lda, BM))) return rc;
+    if ((rc = tma_encode_2d(&p->tmB, Bw, N, K, ldb, p->pair ? p->BN / 2 : p->BN))) return rc;
     p->grid = p->pair ? dim3((p->mtiles + 1) / 2 * 2, ceil_div(N, p->BN)) : dim3(ceil_div(N, p->BN), p->mtiles);
     finish_plan(p);
     return D2S_OK;
@@ -781,7 +781,7 @@ int gemm_plan_conv3x3(GemmPlan *p, const __half *A, const ConvGeom &g, const __h
     p->kblocks = 9 * (g.Cp / BK);
     p->pair = use_pair(p->BN, p->mtiles, ceil_div(N, p->BN));
     if ((rc = encode_nhwc(&p->tmA, A, g, p->TW, p->TH))) return rc;
-    if ((rc = encode_2d(&p->tmB, Bw, N, p->K, p->K, p->pair ? p->BN / 2 : p->BN))) return rc;
+    if ((rc = tma_encode_2d(&p->tmB, Bw, N, p->K, p->K, p->pair ? p->BN / 2 : p->BN))) return rc;
     p->grid = p->pair ? dim3((p->mtiles + 1) / 2 * 2, ceil_div(N, p->BN)) : dim3(ceil_div(N, p->BN), p->mtiles);
     finish_plan(p);
     return D2S_OK;

@@ -58,6 +58,8 @@ int gemm_plan_linear(GemmPlan *p, const __half *A, int lda, const __half *Bw, in
 // A: NHWC fp16 [B,H,W,Cp]; Bw: [N, 9*Cp] with k = (ky*3+kx)*Cp + c.  Output rows are pixels (b,y,x) -> (b*H+y)*W+x.
 int gemm_plan_conv3x3(GemmPlan *p, const __half *A, const ConvGeom &g, const __half *Bw, int N, const GemmEpi &epi);
 int gemm_launch(const GemmPlan *p, cudaStream_t stream);
+// fp16 [rows, cols] row-major (pitch ld_elems) -> tensor map with 64-column x box_rows boxes, SWIZZLE_128B (after gemm_init())
+int tma_encode_2d(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows);
 void gemm_set_plan_policy(int policy);   // 0 latency, 1 throughput: tile-shape heuristics of the plans built next on this thread
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes (idempotent)
 

@@ -1,11 +1,19 @@
 // Non-GEMM layers of the depth network (all memory/latency bound, warp-shuffle reductions).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace d2s {
 
 // attention.cu
 int attention_launch(const __half *qkv, __half *out, int B, int N, int D, int heads, cudaStream_t stream);
+
+// attention_tc.cu — the same attention on tcgen05 (plan = tensor maps over qkv / the V^T scratch; vt: attention_tc_vt_elems() halves, zeroed)
+struct AttnTcPlan { CUtensorMap tmQK, tmV; const __half *qkv; __half *vt, *out; int B, N, D, heads, Npad; };
+size_t attention_tc_vt_elems(int B, int N, int heads);
+int attention_tc_plan(AttnTcPlan *p, const __half *qkv, __half *vt, __half *out, int B, int N, int D, int heads);
+int attention_tc_launch(const AttnTcPlan *p, cudaStream_t stream);
 
 // layers.cu
 // LayerNorm over the last dim of fp32 rows -> fp16 (GEMM A operand).  Row r of the output reads input row

@@ -94,8 +94,10 @@ def test_conv3x3_implicit_gemm(cuda_device, B, H, W, Cin, N, act):
     assert torch.equal(out_relu, F.relu(out))
 
 
-@pytest.mark.parametrize("B,N,heads", [(1, 778, 6), (2, 1370, 2), (1, 36, 2), (3, 64, 1), (1, 65, 12)])
-def test_attention(cuda_device, B, N, heads):
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("B,N,heads", [(1, 778, 6), (2, 1370, 2), (1, 36, 2), (3, 64, 1), (1, 65, 12), (8, 778, 16), (1, 128, 1), (1, 129, 3)])
+def test_attention(cuda_device, monkeypatch, B, N, heads, impl):
+    monkeypatch.setenv("D2S_ATTN", impl)   # tcgen05 (attention_tc.cu, the default) | mma (the mma.sync kernel)
     from desktop2stereo_b200 import _lib
     D = heads * 64
     g = torch.Generator(device="cpu").manual_seed(N + heads)
