@@ -347,10 +347,11 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     for (int i = 0; i < 4; ++i) TRY(plan_alloc(sp, &feat[i], (size_t)BP * D));
     const float eps = c.layer_norm_eps;
     const int heads = c.heads, mlp = c.mlp_hidden;
-    // attention: the mma.sync flash kernel by default; D2S_ATTN=tcgen05 selects the tcgen05 kernel (attention_tc.cu: correct, but
-    // not faster yet — 24 + 10 us (V^T transpose) vs 18 us at B=1 x 6 heads, 98 + 19 vs 106 us at B=8 x 16 heads)
+    // attention: the tcgen05 kernel (attention_tc.cu; V^T comes from the qkv GEMM's epilogue) when there are enough 128-query
+    // tiles to fill the GPU (71 vs 101 us per layer at B = 8 x 16 heads), else the mma.sync flash kernel (equal at B = 1, and
+    // its 64-query tiles spread over more SMs).  D2S_ATTN=tcgen05 | mma forces one.
     const char *attn_env = getenv("D2S_ATTN");
-    const bool attn_tc = attn_env && attn_env[0] == 't';
+    const bool attn_tc = attn_env && attn_env[0] ? attn_env[0] == 't' : (long long)B * heads * ceil_div(N, 128) >= 2 * kNumSMs;
     AttnTcPlan attn{};
     if (attn_tc) {
         __half *vt16;
@@ -361,8 +362,9 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
         const LayerW lw = e->layers[l];
         sp->ops.push_back([=](cudaStream_t st) { return layernorm_launch(X, lw.ln1_w, lw.ln1_b, ln16, M, D, eps, 0, N, st); });
         GemmEpi eq; eq.bias = lw.qkv_b; eq.c16 = qkv16; eq.ldc = 3 * D;
+        if (attn_tc) { eq.vt = attn.vt; eq.vt_col0 = 2 * D; eq.vt_tokens = N; eq.vt_heads = heads; eq.vt_npad = attn.Npad; }
         TRY(add_linear(sp, ln16, D, lw.qkv_w, D, M, 3 * D, D, eq));
-        if (attn_tc) sp->ops.push_back([=](cudaStream_t st) { return attention_tc_launch(&attn, st); });
+        if (attn_tc) sp->ops.push_back([=](cudaStream_t st) { return attention_tc_launch(&attn, st, true); });
         else sp->ops.push_back([=](cudaStream_t st) { return attention_launch(qkv16, att16, B, N, D, heads, st); });
         GemmEpi epj; epj.bias = lw.proj_b; epj.x32 = X; epj.ldc = D;   // LayerScale folded; X += ...
         TRY(add_linear(sp, att16, D, lw.proj_w, D, M, D, D, epj));

@@ -62,7 +62,7 @@ enum { MODE_C16 = 0,    // fp16 store of act(acc + bias) (+ fp16 residuals, + op
 // loaded by the caller (so that their global-memory round trips overlap instead of forming a chain).
 template <int ACT, int MODE>
 __device__ __forceinline__ void epilogue8(const GemmEpi &e, float (&v)[8], const float *sb, uint4 r1, uint4 r2, long long off, int n,
-                                          float &head_acc) {
+                                          float &head_acc, long long orow = 0) {
     {
         float4 b0 = *(const float4 *)sb, b1 = *(const float4 *)(sb + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
@@ -99,6 +99,13 @@ __device__ __forceinline__ void epilogue8(const GemmEpi &e, float (&v)[8], const
 #pragma unroll
         for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
         *(uint4 *)(e.c16 + off) = *(const uint4 *)h;
+        if (e.vt && n >= e.vt_col0) {   // V^T for the tcgen05 attention: adjacent lanes are adjacent tokens, so each store instruction is contiguous
+            const int img = (int)(orow / e.vt_tokens), tok = (int)(orow - (long long)img * e.vt_tokens), cv = n - e.vt_col0;
+            __half *dst = e.vt + ((size_t)(img * e.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * e.vt_npad + tok;
+            const __half *hv = (const __half *)h;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) dst[(size_t)t * e.vt_npad] = hv[t];
+        }
         if (e.c16_relu) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) h[t] = __hmax2(h[t], __float2half2_rn(0.f));
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                     float v[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(raw[j * 8 + t]);
-                    epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
+                    epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc, orow);
                 }
             }
         } else {
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
                     if (z == 0) { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
                     else { v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w; }
                 }
-                if (live) epilogue8<ACT, MODE>(e, v, s_bias + u * 8, r1, r2, off, n, head_acc);
+                if (live) epilogue8<ACT, MODE>(e, v, s_bias + u * 8, r1, r2, off, n, head_acc, orow);
             }
         }
         ptx::cluster_sync();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(kPersistThreads) gemm_tc_persistent_kernel(con
                     float v[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(raw[j * 8 + t]);
-                    epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc);
+                    epilogue8<ACT, MODE>(e, v, s_bias + c * 32 + j * 8, r1[j], r2[j], off0 + j * 8, n0 + j * 8, head_acc, orow);
                 }
             }
         }

@@ -18,6 +18,10 @@ struct GemmEpi {
     const __half *res2 = nullptr;
     __half *c16 = nullptr;           // fp16 output
     __half *c16_relu = nullptr;      // optional relu(v) copy (input of the next pre-activation conv)
+    // optional transposed copy of the columns >= vt_col0 (the V third of a fused qkv projection) for the tcgen05 attention:
+    // vt[((row / vt_tokens) * vt_heads + head) * 64 + d][row % vt_tokens], row pitch vt_npad, head = (col - vt_col0) / 64
+    __half *vt = nullptr;
+    int vt_col0 = 0, vt_tokens = 1, vt_heads = 1, vt_npad = 0;
     float *x32 = nullptr;            // fp32 residual stream: x32[row, col] += v   (x32_assign: = v)
     int x32_assign = 0;
     float *c32 = nullptr;            // fp32 output (plain store)

@@ -13,7 +13,7 @@ int attention_launch(const __half *qkv, __half *out, int B, int N, int D, int he
 struct AttnTcPlan { CUtensorMap tmQK, tmV; const __half *qkv; __half *vt, *out; int B, N, D, heads, Npad; };
 size_t attention_tc_vt_elems(int B, int N, int heads);
 int attention_tc_plan(AttnTcPlan *p, const __half *qkv, __half *vt, __half *out, int B, int N, int D, int heads);
-int attention_tc_launch(const AttnTcPlan *p, cudaStream_t stream);
+int attention_tc_launch(const AttnTcPlan *p, cudaStream_t stream, bool vt_ready = false);   // vt_ready: V^T was already written (fused qkv epilogue)
 
 // layers.cu
 // LayerNorm over the last dim of fp32 rows -> fp16 (GEMM A operand).  Row r of the output reads input row

@@ -41,6 +41,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// wait with back-off: for single-thread producer / issuer roles whose spinning would otherwise steal issue slots from the
+// compute warps that share their scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+
 // ---- thread-block clusters / distributed shared memory ----
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");

@@ -118,3 +118,19 @@ def test_engine_throughput_policy(cuda_device):
     print("latency vs ref", _rel(lat, ref), "throughput vs ref", _rel(thr, ref), "latency vs throughput", _rel(thr, lat))
     assert _rel(lat, ref) <= 5e-3 and _rel(thr, ref) <= 5e-3
     eng.close()
+
+
+@pytest.mark.parametrize("case", MODEL_CASES[:2] + MODEL_CASES[2:], ids=lambda c: c[0])
+def test_engine_tcgen05_attention(cuda_device, monkeypatch, golden_dir, case):
+    """The tcgen05 attention path (chosen automatically for large batches; forced here): V^T written by the qkv GEMM's epilogue,
+    QK^T / PV on tensor cores.  Same parity bound as the default path, deterministic."""
+    from desktop2stereo_b200.engine import B200Engine
+    monkeypatch.setenv("D2S_ATTN", "tcgen05")
+    name, variant, tiny, seed, B, H, W, stride = case
+    gold = torch.from_numpy(np.load(os.path.join(golden_dir, "model.npz"))[name])
+    eng = B200Engine.from_hf_model(make_hf_model(variant, seed, tiny), cuda_device, out_dtype=torch.float32)
+    x = torch.from_numpy(model_input(seed, B, H, W)).to(cuda_device)
+    out = eng(x).clone()
+    assert _rel(out.cpu()[:, ::stride, ::stride], gold) <= 5e-3
+    assert torch.equal(eng(x), out)
+    eng.close()
