@@ -522,5 +522,30 @@ def run_vda1080(args):
     return 0
 
 
+def _main_with_clean_stdout():
+    """Libraries (NCCL's version banner, torchrun's notices) write to fd 1; the contract is ONE JSON line on stdout.  Everything
+    written while the benchmark runs is diverted to stderr, and only the result line goes to the real stdout."""
+    import io
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    old = sys.stdout
+    sys.stdout = buf
+    rc = 1
+    try:
+        rc = main()
+    finally:
+        sys.stdout = old
+        sys.stdout.flush()
+        os.dup2(real, 1)
+        os.close(real)
+        for l in buf.getvalue().splitlines():
+            if l.strip():
+                (sys.stdout if l.lstrip().startswith("{") else sys.stderr).write(l + "\n")
+        sys.stdout.flush()
+    return rc
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_main_with_clean_stdout())
