@@ -338,6 +338,7 @@ def main():
                    "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms,
                    "stage_ms_mean": serial_stage_mean},
         "roofline": roofline_net, "roofline_warp": roofline_warp, "roofline_net": roofline_net,
+        "roofline_gemm": gemm_rooflines(dev, peaks, src),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -349,6 +350,43 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def gemm_rooflines(dev, peaks, src):
+    """The tcgen05 GEMM kernel alone, timed live with CUDA events around a graph of back-to-back launches (so that host launch
+    cost is not what is measured): the headline workload's own shapes (M = 778 token rows: latency-bound) and the same layers at
+    batch 8 (M = 6224: persistent kernel).  Peak = the measured cuBLAS bf16 BURST figure (a kernel timed in isolation)."""
+    import torch
+    from desktop2stereo_b200 import _lib
+    L = _lib.lib()
+    out = []
+    for (name, M, N, K, x32) in [("qkv, batch 1", 778, 2304, 768, False), ("fc2 (+residual stream), batch 1", 778, 768, 3072, True),
+                                 ("qkv, batch 8 (ViT-L)", 6224, 3072, 1024, False), ("fc1, batch 8 (ViT-L)", 6224, 4096, 1024, False)]:
+        A = torch.randn(M, K, device=dev).half(); B = torch.randn(N, K, device=dev).half() * (K ** -0.5); bias = torch.randn(N, device=dev)
+        C = torch.empty(M, N, device=dev, dtype=torch.float16); X = torch.zeros(M, N, device=dev)
+        st = torch.cuda.Stream(dev)
+        iters = 20
+
+        def call():
+            _lib.check(L.d2s_debug_gemm(A.data_ptr(), B.data_ptr(), bias.data_ptr(), None if x32 else C.data_ptr(), M, N, K, 0,
+                                        X.data_ptr() if x32 else None, torch.cuda.current_stream(dev).cuda_stream))
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                call()
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(iters):
+                    call()
+            g.replay(); st.synchronize()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(st); g.replay(); e_.record(st); st.synchronize()
+        us = s_.elapsed_time(e_) * 1e3 / iters
+        tf = 2.0 * M * N * K / us / 1e6
+        out.append({"kernel": "gemm_tc_kernel / gemm_tc_persistent_kernel (tcgen05)", "layer": name, "M": M, "N": N, "K": K, "bound": "tensor",
+                    "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "duration_us": us,
+                    "peak_source": src + " (burst)", "timed": "graph of %d back-to-back launches, CUDA events on its stream, L2-warm" % iters})
+    return out
 
 
 def load_peaks():
