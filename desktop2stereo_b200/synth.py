@@ -20,6 +20,10 @@ DA_V2_VARIANTS = {
 }
 
 
+# a small DA-V2 configuration for fast parity tests (the architecture, scaled down)
+TINY_CFG = dict(hidden=128, layers=4, heads=2, out_indices=[1, 2, 3, 4], neck=[24, 48, 96, 192], fusion=64)
+
+
 def make_hf_model(variant: str = "Small", seed: int = 0, tiny: dict | None = None):
     """Seeded random-init HF DepthAnythingForDepthEstimation (fp32, eval).
 

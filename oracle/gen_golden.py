@@ -223,7 +223,7 @@ def gen_post_metric(depth_mod):
     print("post_metric.npz written")
 
 
-TINY = dict(hidden=128, layers=4, heads=2, out_indices=[1, 2, 3, 4], neck=[24, 48, 96, 192], fusion=64)
+from desktop2stereo_b200.synth import TINY_CFG as TINY  # noqa: E402
 MODEL_CASES = [  # (name, variant, tiny cfg, seed, B, H, W, stored stride)
     ("tiny_70x98", "Small", TINY, 3, 2, 70, 98, 1),
     ("tiny_518", "Small", TINY, 4, 1, 518, 518, 7),

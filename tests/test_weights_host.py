@@ -1,0 +1,50 @@
+"""Host-side weight packing (no GPU): blob sizes follow the documented order, LayerScale folding, the VDA position tables."""
+import numpy as np
+import torch
+
+from desktop2stereo_b200.synth import TINY_CFG, VDA_ENCODERS, make_hf_model, make_vda_state_dict, param_shapes
+from desktop2stereo_b200.weights import config_for_vda, config_from_hf, pack_state_dict, pack_vda_state_dict
+
+
+def _dav2_count(D, L, c, F):
+    n = D * 588 + D + D + (1 + 37 * 37) * D
+    n += L * (2 * D + 3 * D * D + 3 * D + D * D + D + 2 * D + 4 * D * D + 4 * D + 4 * D * D + D) + 2 * D
+    n += sum(ci * D + ci for ci in c) + c[0] * c[0] * 16 + c[0] + c[1] * c[1] * 4 + c[1] + c[3] * c[3] * 9 + c[3]
+    n += sum(F * ci * 9 for ci in c) + 4 * (F * F + F + 4 * (F * F * 9 + F))
+    n += (F // 2) * F * 9 + F // 2 + 32 * (F // 2) * 9 + 32 + 32 + 1
+    return n
+
+
+def test_pack_dav2_blob_size_and_layerscale():
+    m = make_hf_model("Small", 0, TINY_CFG)
+    cfg = config_from_hf(m.config)
+    blob = pack_state_dict(m.state_dict(), cfg)
+    assert blob.dtype == np.float32 and blob.size == _dav2_count(cfg.hidden, cfg.layers, list(cfg.neck), cfg.fusion)
+    sd = m.state_dict()
+    D = cfg.hidden
+    off = D * 588 + D + D + (1 + 37 * 37) * D + 2 * D + 3 * D * D + 3 * D       # first layer's proj weight
+    w = sd["backbone.encoder.layer.0.attention.output.dense.weight"].numpy() * sd["backbone.encoder.layer.0.layer_scale1.lambda1"].numpy()[:, None]
+    assert np.array_equal(blob[off:off + D * D].reshape(D, D), w.astype(np.float32))
+    assert cfg.temporal == 0 and cfg.pos_interp_offset == 0.0
+
+
+def test_pack_vda_blob():
+    enc = "vits"
+    sd = make_vda_state_dict(enc, 3)
+    assert [n for n, _ in param_shapes(enc)] == list(sd.keys())
+    cfg = config_for_vda(enc)
+    e = VDA_ENCODERS[enc]
+    assert cfg.temporal == 1 and abs(cfg.pos_interp_offset - 0.1) < 1e-7 and list(cfg.out_indices) == [t + 1 for t in e["taps"]]
+    blob = pack_vda_state_dict(sd, cfg)
+    base = _dav2_count(cfg.hidden, cfg.layers, list(cfg.neck), cfg.fusion)
+    temporal = 0
+    for C in (e["out_channels"][2], e["out_channels"][3], e["features"], e["features"]):
+        temporal += 2 * C + C * C + C + 2 * (2 * C + 3 * C * C + 32 * 3 * C + C * C + C) + 2 * C + 8 * C * C + 8 * C + 4 * C * C + C + C * C + C
+    assert blob.size == base + temporal
+    # the position tables are pe @ [to_q; to_k; to_v]^T (the projections are linear and bias-free)
+    C = e["out_channels"][2]
+    ab = "head.motion_modules.0.temporal_transformer.transformer_blocks.0.attention_blocks.0."
+    qkv = torch.cat([sd[ab + "to_q.weight"], sd[ab + "to_k.weight"], sd[ab + "to_v.weight"]], 0)
+    want = (sd[ab + "pos_encoder.pe"][0].double() @ qkv.double().t()).float().numpy()
+    off = base + 2 * C + C * C + C + 2 * C + 3 * C * C
+    assert np.allclose(blob[off:off + 32 * 3 * C].reshape(32, 3 * C), want, rtol=0, atol=1e-6)
