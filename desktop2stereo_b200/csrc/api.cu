@@ -6,6 +6,7 @@
 namespace d2s {
 thread_local std::string g_last_error;
 std::atomic<long long> g_launch_count{0};
+thread_local bool g_pdl = false;
 
 int set_error(int code, const char *fmt, ...) {
     char buf[1024];

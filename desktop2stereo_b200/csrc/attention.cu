@@ -49,6 +49,7 @@ __device__ __forceinline__ void load_tile(__half *s, const __half *g, int ld, in
 
 __global__ void __launch_bounds__(128) attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int N, int D,
                                                         float scale_log2e) {
+    pdl_sync();
     __shared__ __align__(16) __half sQ[kAttBQ * kAttPitch];
     __shared__ __align__(16) __half sK[2][kAttBK * kAttPitch];
     __shared__ __align__(16) __half sV[2][kAttBK * kAttPitch];

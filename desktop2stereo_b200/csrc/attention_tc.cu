@@ -33,6 +33,7 @@ struct AttnArgs {
 
 // V third of qkv16 [B*N, 3D] -> vt16 [B, heads, 64, Npad] (keys contiguous); columns N..Npad-1 stay zero
 __global__ void v_transpose_kernel(const __half *__restrict__ qkv, __half *__restrict__ vt, int N, int D, int heads, int Npad) {
+    pdl_sync();
     __shared__ __half tile[64][66];
     const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 64;
     const __half *src = qkv + (size_t)b * N * 3 * D + 2 * D + h * 64;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) attention_tc_kernel(const __gri
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tS = tmem_base, tPV = tmem_base + 128;
+    pdl_sync();   // barrier init / TMEM allocation above ran under the previous kernel's tail; qkv and V^T are read below
 
     if (warp == 0) {
         if (lane == 0) {

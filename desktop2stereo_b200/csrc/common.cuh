@@ -35,11 +35,34 @@ int set_error(int code, const char *fmt, ...);
         if (!(cond)) return ::d2s::set_error(D2S_ERR_INVALID, __VA_ARGS__);    \
     } while (0)
 
+// Programmatic dependent launch (PDL).  While the engine records or runs a plan, g_pdl is set and every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: kernel N+1 may be scheduled as soon as every CTA of kernel N has executed
+// griddepcontrol.launch_dependents, runs its prologue (barrier init, TMEM allocation, tensor-map prefetch, index maths) under
+// kernel N's tail, and blocks in griddepcontrol.wait until kernel N has completed and flushed its writes.  Every kernel of the
+// plan therefore starts with pdl_sync() before it touches data a predecessor produced (a no-op for ordinary launches).
+extern thread_local bool g_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_launch_dependents(); }
+#endif
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Every kernel launch of the library goes through this so gpu_launches can be reported.
-#define D2S_LAUNCH(kernel, grid, block, smem, stream, ...)                          \
-    do {                                                                            \
-        kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);   \
-        ::d2s::g_launch_count.fetch_add(1, std::memory_order_relaxed);              \
+#define D2S_LAUNCH(kernel, grid, block, smem, stream, ...)                                                                  \
+    do {                                                                                                                    \
+        (void)::d2s::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__);   \
+        ::d2s::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                                      \
     } while (0)
 
 #define D2S_POST_LAUNCH() D2S_CHECK_CUDA(cudaPeekAtLastError())

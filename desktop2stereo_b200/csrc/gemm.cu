@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
+    pdl_sync();   // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel; operands are read below
     if (threadIdx.x == 0) D2S_STAMP(1);
 
     // conv tile -> (image, y0, x0)
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(kPersistThreads) gemm_tc_persistent_kernel(con
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    pdl_sync();
 
     // tile walk: unit = one CTA tile, or one pair tile (two M tiles); M-fastest
     const int units_m = PAIR ? (g.mtiles + 1) / 2 : g.mtiles;
@@ -810,10 +812,13 @@ int gemm_launch(const GemmPlan *p, cudaStream_t stream) {
     if (!fn) return set_error(D2S_ERR_UNSUPPORTED, "gemm: no kernel variant for BN=%d act=%d mode=%d", p->BN, p->epi.act, mode);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = p->grid; cfg.blockDim = dim3(p->persist ? kPersistThreads : kGemmThreads); cfg.dynamicSmemBytes = p->smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL (common.cuh), appended below when enabled
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K: the CTAs of one output tile are one cluster
     attr[0].val.clusterDim.x = p->pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)p->splits;   // (a pair never splits K)
-    cfg.attrs = attr; cfg.numAttrs = (p->splits > 1 || p->pair) ? 1 : 0;
+    const bool clustered = p->splits > 1 || p->pair;
+    cfg.attrs = clustered ? attr : attr + 1; cfg.numAttrs = (clustered ? 1 : 0) + (g_pdl ? 1 : 0);
     cudaError_t le = cudaLaunchKernelEx(&cfg, fn, a);
     if (le != cudaSuccess) {
         int nc = -1;

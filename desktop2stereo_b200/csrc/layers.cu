@@ -8,6 +8,7 @@ namespace d2s {
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, __half *__restrict__ y, int rows, int D,
                                                         float eps, int skip_cls, int tokens_per_img) {
+    pdl_sync();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     long long in_row = row;
@@ -56,6 +57,7 @@ int layernorm_launch(const float *x, const float *gamma, const float *beta, __ha
 // ---- patch embedding as GEMM: im2col of non-overlapping 14x14 patches (HF dinov2:139-149) ----
 template <typename T>
 __global__ void patch_im2col_kernel(const T *__restrict__ pix, __half *__restrict__ out, int B, int H, int W, int patch, int Kp) {
+    pdl_sync();
     const int ph = H / patch, pw = W / patch, K = 3 * patch * patch;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * ph * pw * K;
@@ -81,6 +83,7 @@ int patch_im2col_launch(const void *pix, int in_dtype, __half *out, int B, int H
 // ---- cls token + position embeddings (HF dinov2:97-116) ----
 __global__ void assemble_tokens_kernel(const __half *__restrict__ patches, const float *__restrict__ cls, const float *__restrict__ pos,
                                        float *__restrict__ x, int B, int P, int D) {
+    pdl_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * (P + 1) * D;
     if (i >= total) return;
@@ -140,6 +143,7 @@ int pos_embed_interp_launch(const float *pos_table, float *pos_out, int grid, in
 
 // ---- ConvTranspose (kernel == stride) scatter ----
 __global__ void pixel_shuffle_kernel(const __half *__restrict__ in, __half *__restrict__ out, int B, int h, int w, int f, int C, int Cp) {
+    pdl_sync();
     const int c8 = C / 8;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * h * w * f * f * c8;
@@ -164,6 +168,7 @@ int pixel_shuffle_launch(const __half *gemm_out, __half *out, int B, int h, int 
 
 // ---- explicit im2col for the 3x3 / stride 2 / pad 1 conv of the coarsest reassemble level ----
 __global__ void im2col_s2_kernel(const __half *__restrict__ in, __half *__restrict__ out, int B, int h, int w, int Cp, int oh, int ow) {
+    pdl_sync();
     const int c8 = Cp / 8;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * oh * ow * 9 * c8;
@@ -189,6 +194,7 @@ int im2col_s2_launch(const __half *in, __half *out, int B, int h, int w, int Cp,
 // ---- bilinear upsampling, align_corners=True, NHWC fp16 (ATen upsample_bilinear2d, fp32 accumulate) ----
 __global__ void upsample_nhwc_kernel(const __half *__restrict__ in, __half *__restrict__ out, int B, int h, int w, int C, int oh, int ow,
                                      float rh, float rw) {
+    pdl_sync();
     const int c8 = C / 8;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * oh * ow * c8;
@@ -268,6 +274,7 @@ int convt_weight_launch(const float *src, __half *dst, int Cin, int Cout, int f,
 }
 
 __global__ void relu_copy_kernel(const __half2 *__restrict__ in, __half2 *__restrict__ out, size_t n2) {
+    pdl_sync();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n2) return;
     out[i] = __hmax2(in[i], __float2half2_rn(0.f));

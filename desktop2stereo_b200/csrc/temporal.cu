@@ -18,6 +18,7 @@ namespace d2s {
 // pass 1: per (pixel slice, channel) sums -> per (slice, group) partial sums (fixed order => deterministic)
 constexpr int kGnSlice = 64;   // pixels per block
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half *__restrict__ x, float *__restrict__ part, int d, int C, int Cp) {
+    pdl_sync();
     __shared__ float s_sum[1024], s_sq[1024];
     const int p0 = blockIdx.x * kGnSlice, p1 = min(p0 + kGnSlice, d);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half *__restrict_
 // pass 2: finish the statistics (double, fixed order) and normalise
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half *__restrict__ x, const float *__restrict__ part, const float *__restrict__ w,
                                                        const float *__restrict__ b, __half *__restrict__ y, int d, int C, int Cp, int nslices, float eps) {
+    pdl_sync();
     __shared__ float s_mean[32], s_rstd[32];
     if (threadIdx.x < 32) {
         double s = 0.0, q = 0.0;
@@ -73,6 +75,7 @@ size_t groupnorm32_partial_floats(int d) { return (size_t)ceil_div(d, kGnSlice) 
 
 // ---- GEGLU: [d, 8C] (value | gate) -> value * gelu(gate) [d, 4C]  (attention.py:363-384) ---------------------------------
 __global__ void geglu_kernel(const __half *__restrict__ in, __half *__restrict__ out, long long rows, int inner) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread = 8 channels
     const int n8 = inner / 8;
     if (i >= rows * n8) return;
@@ -99,6 +102,7 @@ int geglu_launch(const __half *in, __half *out, long long rows, int inner, cudaS
 
 // ---- fp32 -> fp16 (GEMM A operand of proj_out) -----------------------------------------------------------------------------
 __global__ void cast_f16_kernel(const float *__restrict__ in, __half *__restrict__ out, long long n4) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 v = ((const float4 *)in)[i];
@@ -123,6 +127,7 @@ int cast_f16_launch(const float *in, __half *out, long long n, cudaStream_t stre
 // seeds its cache with 31 copies of it), position 31 is the newest frame and the only query.
 __global__ void __launch_bounds__(256) temporal_attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ ring, const float *__restrict__ pe,
                                                                  const long long *__restrict__ t_ptr, __half *__restrict__ out, int C, float scale) {
+    pdl_sync();
     extern __shared__ float s_mem[];                 // [8 warps][hd] query  +  [8][32] probabilities
     const int hd = C >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,7 +193,10 @@ int temporal_attention_launch(const __half *qkv, __half *ring, const float *pe, 
     return D2S_OK;
 }
 
-__global__ void frame_counter_kernel(long long *t) { *t += 1; }
+__global__ void frame_counter_kernel(long long *t) {
+    pdl_sync();
+    *t += 1;
+}
 int frame_counter_inc_launch(long long *t, cudaStream_t stream) {
     D2S_LAUNCH(frame_counter_kernel, 1, 1, 0, stream, t);
     D2S_POST_LAUNCH();
