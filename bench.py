@@ -309,7 +309,8 @@ def main():
     net_tflops_iso = gflop / (serial_stage_ms["predict_depth"] * 1e-3) / 1e3
     net_tflops = gflop * args.steps / (ms * 1e-3) / 1e3
     roofline_warp = {"kernel": "warp_sbs_fast_kernel", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "bytes_per_launch": warp_bytes,
+                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": 16.63e6 + 1.22e6, "traffic_note": "dram__bytes_read + dram__bytes_write of one isolated launch under ncu --set full (profiles/r1_warp_v4_ncu_full.txt): the 49.8 MB written stay in the 126 MB L2 during an isolated replay",
+                     "peak_source": src, "bytes_per_launch": warp_bytes,
                      "duration_ms": serial_stage_ms["warp"], "timed": "alone on the GPU (serial leg), CUDA events on its stream, median of %d" % n_serial,
                      "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS"}
     roofline_net = {"kernel": "depth network, one graph launch per frame (preprocess + ViT-B + DPT on gemm_tc_kernel/tcgen05 + postprocess)",
