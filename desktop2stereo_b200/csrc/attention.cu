@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_tile(__half *s, const __half *g, int ld, in
 
 __global__ void __launch_bounds__(128) attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int N, int D,
                                                         float scale_log2e) {
-    pdl_sync();
+    pdl_wait();
     __shared__ __align__(16) __half sQ[kAttBQ * kAttPitch];
     __shared__ __align__(16) __half sK[2][kAttBK * kAttPitch];
     __shared__ __align__(16) __half sV[2][kAttBK * kAttPitch];
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half *__restrict
         }
         __syncthreads();
     }
+    pdl_launch_dependents();
     // finalise: row sums live in quads
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);

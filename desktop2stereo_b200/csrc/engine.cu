@@ -35,6 +35,7 @@ struct Tap { const void *ptr; size_t n; int dtype; };
 struct ShapePlan {
     int B, H, W, in_dtype, out_dtype;
     cudaStream_t stream = nullptr;         // the stream this plan is bound to (temporal engines keep per-stream state)
+    int policy = 0;                        // D2S_POLICY_* the plan was built under
     long long *frame_counter = nullptr;    // temporal: frames seen on this stream (device)
     std::vector<void *> allocs;
     std::vector<std::function<int(cudaStream_t)>> ops;
@@ -479,11 +480,12 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
 }
 
 static int run_ops(ShapePlan *sp, cudaStream_t st) {
-    // Programmatic dependent launch between the kernels of the plan (common.cuh) is wired through every kernel but OFF by default:
-    // measured on B200 it made the frame slower (1.51 vs 1.42 ms alone, 1632 vs 1725 frames/s in flight) — the early-launched
-    // CTAs hold shared memory / TMEM while they wait for their predecessor.  D2S_PDL=1 turns it on.
+    // Programmatic dependent launch between the kernels of the plan (common.cuh; the GEMM and attention kernels release their
+    // dependents when their main loop is over, so the next kernel's prologue runs under their epilogue).  Measured on B200:
+    // +3.6 % frames/s with 8 frames in flight (1794 vs 1731), but +0.07 ms for one frame alone (1.48 vs 1.42 ms) — so it is on for
+    // throughput-policy plans and off for latency-policy plans.  D2S_PDL=0 | 1 forces it.
     const char *pe = getenv("D2S_PDL");
-    g_pdl = pe && pe[0] == '1';
+    g_pdl = pe && pe[0] ? pe[0] == '1' : sp->policy == D2S_POLICY_THROUGHPUT;
     int rc = D2S_OK;
     for (auto &op : sp->ops)
         if ((rc = op(st))) break;
@@ -553,7 +555,7 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
         // first frame of this shape: allocate buffers, encode tensor maps, capture the graph (the only host-synchronous path,
         // like the reference's lazy engine build at depth.py:1842-1862)
         std::unique_ptr<ShapePlan> sp(new ShapePlan());
-        sp->B = B; sp->H = H; sp->W = W; sp->in_dtype = in_dtype; sp->out_dtype = out_dtype; sp->stream = st;
+        sp->B = B; sp->H = H; sp->W = W; sp->in_dtype = in_dtype; sp->out_dtype = out_dtype; sp->stream = st; sp->policy = h->policy;
         gemm_set_plan_policy(h->policy);
         int rc = build_plan(h, sp.get());
         gemm_set_plan_policy(0);

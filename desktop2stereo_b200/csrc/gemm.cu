@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
-    pdl_sync();   // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel; operands are read below
+    pdl_wait();   // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel; operands are read below
     if (threadIdx.x == 0) D2S_STAMP(1);
 
     // conv tile -> (image, y0, x0)
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
         const uint4 z4 = make_uint4(0, 0, 0, 0);
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
+        pdl_launch_dependents();   // the main loop is over: the next kernel's CTAs may move in and run their prologue under this epilogue
         if (threadIdx.x == 64) D2S_STAMP(6);
         float head_acc = 0.f;
         if (!fixup) {
