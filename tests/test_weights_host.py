@@ -48,3 +48,23 @@ def test_pack_vda_blob():
     want = (sd[ab + "pos_encoder.pe"][0].double() @ qkv.double().t()).float().numpy()
     off = base + 2 * C + C * C + C + 2 * C + 3 * C * C
     assert np.allclose(blob[off:off + 32 * 3 * C].reshape(32, 3 * C), want, rtol=0, atol=1e-6)
+
+
+def test_checkpoint_loaders_round_trip(tmp_path):
+    """config.json + model.safetensors (HF snapshot layout) and a .pth state_dict (VDA) give the same blob as packing the live
+    state_dict."""
+    from safetensors.torch import save_file
+    from desktop2stereo_b200.checkpoints import load_hf_checkpoint, load_vda_checkpoint
+    m = make_hf_model("Small", 1, TINY_CFG)
+    d = tmp_path / "hf"
+    d.mkdir()
+    (d / "config.json").write_text(m.config.to_json_string())
+    save_file({k: v.contiguous() for k, v in m.state_dict().items()}, str(d / "model.safetensors"))
+    blob, cfg = load_hf_checkpoint(str(d))
+    want_cfg = config_from_hf(m.config)
+    assert np.array_equal(blob, pack_state_dict(m.state_dict(), want_cfg))
+    assert (cfg.hidden, cfg.layers, cfg.heads, list(cfg.neck), cfg.fusion) == (want_cfg.hidden, want_cfg.layers, want_cfg.heads, list(want_cfg.neck), want_cfg.fusion)
+    sd = make_vda_state_dict("vits", 5)
+    torch.save(sd, str(tmp_path / "video_depth_anything_vits.pth"))
+    blob2, cfg2 = load_vda_checkpoint(str(tmp_path / "video_depth_anything_vits.pth"), "vits")
+    assert cfg2.temporal == 1 and np.array_equal(blob2, pack_vda_state_dict(sd, config_for_vda("vits")))
