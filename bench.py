@@ -220,7 +220,7 @@ def main():
     def stage_stats(trace):
         """per-stage device time from the events recorded on each frame's stream: median (robust to a host hiccup) and mean"""
         torch.cuda.synchronize()
-        st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in trace])
+        st = np.array([list(e) if not hasattr(e[0], "elapsed_time") else [e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in trace])
         names = ["process", "predict_depth", "warp"]
         return dict(zip(names, np.median(st, 0).tolist())), dict(zip(names, st.mean(0).tolist()))
 

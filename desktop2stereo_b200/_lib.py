@@ -53,6 +53,17 @@ class PostParams(C.Structure):
                 ("ema_alpha", C.c_float), ("out_lowres", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class PipeConfig(C.Structure):
+    _fields_ = [("frame_h", C.c_int32), ("frame_w", C.c_int32), ("channels", C.c_int32), ("target_height", C.c_int32),
+                ("rgb_dtype", C.c_int32), ("depth_resolution", C.c_int32), ("patch", C.c_int32),
+                ("mean", C.c_float * 3), ("std", C.c_float * 3), ("metric", C.c_int32), ("percentile", C.c_float),
+                ("subsample_cap", C.c_int32), ("gamma", C.c_float), ("foreground_scale", C.c_float), ("aa_strength", C.c_float),
+                ("use_temporal_smooth", C.c_int32), ("ema_alpha", C.c_float),
+                ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
+                ("display_mode", C.c_int32), ("fill_16_9", C.c_int32), ("out_dtype", C.c_int32), ("slots", C.c_int32),
+                ("host_io", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
 # every symbol include/d2s_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "d2s_sbs_out_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -67,12 +78,22 @@ SYMBOLS = {
     "d2s_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "d2s_set_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "d2s_reset_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "d2s_release_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "d2s_debug_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
     "d2s_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "d2s_launch_count": (C.c_int64, []),
     "d2s_postprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "d2s_postprocess": (C.c_int, [C.POINTER(PostParams), C.c_void_p]),
     "d2s_overlay_fps": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_char_p, C.c_void_p]),
+    "d2s_pipe_create": (C.c_int, [C.c_void_p, C.POINTER(PipeConfig), C.POINTER(C.c_void_p)]),
+    "d2s_pipe_destroy": (C.c_int, [C.c_void_p]),
+    "d2s_pipe_geometry": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_size_t)] * 2),
+    "d2s_pipe_slot_buffers": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 6),
+    "d2s_pipe_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "d2s_pipe_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "d2s_pipe_reset": (C.c_int, [C.c_void_p]),
+    "d2s_pipe_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "d2s_pipe_slot_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "d2s_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "d2s_debug_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),

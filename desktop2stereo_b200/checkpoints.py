@@ -27,9 +27,10 @@ def load_hf_checkpoint(path: str):
     if not files:
         raise FileNotFoundError(f"no .safetensors file under {path}")
     for name in files:
-        with safe_open(os.path.join(path, name), framework="np") as st:
+        # framework="pt": fp16 AND bf16 snapshots load (numpy has no bfloat16); everything is widened to fp32 for packing
+        with safe_open(os.path.join(path, name), framework="pt") as st:
             for k in st.keys():
-                sd[k] = np.asarray(st.get_tensor(k), dtype=np.float32)
+                sd[k] = st.get_tensor(k).float().numpy()
     return pack_state_dict(sd, cfg), cfg
 
 

@@ -13,84 +13,7 @@
 // [3D, D] matrix, ConvTranspose(k == stride) is a GEMM followed by a pixel shuffle, 3x3 convs are implicit GEMMs whose
 // A operand is fetched by 4-D TMA boxes (out-of-bounds = zero = padding), the final 1x1 conv + ReLU lives in the epilogue
 // of the last 3x3 conv.  One plan (buffers + tensor maps + CUDA graph) is built per (B, H, W) and replayed per frame.
-#include <cstdlib>
-#include <cstring>
-#include <deque>
-#include <functional>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "gemm.cuh"
-#include "layers.cuh"
-
-namespace d2s {
-
-static int round_up(int x, int a) { return (x + a - 1) / a * a; }
-
-struct Tap { const void *ptr; size_t n; int dtype; };
-
-struct ShapePlan {
-    int B, H, W, in_dtype, out_dtype;
-    cudaStream_t stream = nullptr;         // the stream this plan is bound to (temporal engines keep per-stream state)
-    int policy = 0;                        // D2S_POLICY_* the plan was built under
-    long long *frame_counter = nullptr;    // temporal: frames seen on this stream (device)
-    std::vector<void *> allocs;
-    std::vector<std::function<int(cudaStream_t)>> ops;
-    std::deque<GemmPlan> gemms;            // stable addresses: the op lambdas hold pointers into it
-    std::map<std::string, Tap> taps;
-    void *in_stage = nullptr, *out_stage = nullptr;
-    size_t in_bytes = 0, out_bytes = 0, total_bytes = 0;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    ~ShapePlan() {
-        if (exec) cudaGraphExecDestroy(exec);
-        if (graph) cudaGraphDestroy(graph);
-        for (void *p : allocs) cudaFree(p);
-    }
-};
-
-struct LayerW {
-    float *ln1_w, *ln1_b, *qkv_b, *proj_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;
-    __half *qkv_w, *proj_w, *fc1_w, *fc2_w;
-};
-struct RcuW { __half *c1_w, *c2_w; float *c1_b, *c2_b; };
-struct FusionW { __half *proj_w; float *proj_b; RcuW rl1, rl2; };
-struct TAttnW { float *ln_w, *ln_b, *pe, *out_b; __half *qkv_w, *out_w; };          // pe: [32, 3C] = pe @ {q,k,v}^T
-struct TemporalW {                                                                   // one TemporalModule (motion_module.py:31-134)
-    int C;
-    float *gn_w, *gn_b, *in_b, *ffln_w, *ffln_b, *ff1_b, *ff2_b, *out_b;
-    __half *in_w, *ff1_w, *ff2_w, *out_w;
-    TAttnW att[2];
-};
-
-}  // namespace d2s
-
-struct d2s_engine {
-    d2s_model_config cfg;
-    int device;
-    int D, L, P14, Kpatch;            // Kpatch: 588 padded to 640
-    int c[4], cp[4], F, Fh, Fhp;      // neck channels (+ padded), fusion width, head width (+ padded)
-    std::vector<void *> allocs;
-    size_t weight_bytes = 0;
-    // weights
-    __half *patch_w; float *patch_b, *cls, *pos_table;
-    std::vector<d2s::LayerW> layers;
-    float *norm_w, *norm_b;
-    __half *re_proj_w[4]; float *re_proj_b[4];
-    __half *up0_w, *up1_w, *dn3_w; float *up0_b, *up1_b, *dn3_b;   // up biases are expanded to f*f*C
-    __half *neck_w[4];
-    d2s::FusionW fus[4];
-    __half *head_c1_w, *head_c2_w; float *head_c1_b, *head_c2_b, *head_c3_w; float head_c3_b;
-    d2s::TemporalW tm[4];                                              // cfg.temporal only
-    std::map<std::vector<long long>, std::unique_ptr<d2s::ShapePlan>> plans;   // keyed by shape, dtypes AND stream
-    std::mutex mu;
-    d2s::ShapePlan *last = nullptr;
-    bool use_graph = true;
-    int policy = 0;                      // D2S_POLICY_LATENCY / D2S_POLICY_THROUGHPUT for the plans built next
-};
+#include "engine.cuh"
 
 namespace d2s {
 
@@ -236,6 +159,24 @@ static int plan_alloc(ShapePlan *sp, T **p, size_t count) {
     return D2S_OK;
 }
 
+// the next K'|V' ring of the plan's stream state (allocated by the first plan built for this video, found again by the others)
+static int state_ring(ShapePlan *sp, __half **p, size_t elems) {
+    StreamState *ss = sp->state;
+    if (!ss) return set_error(D2S_ERR_INVALID, "temporal plan without a stream state");
+    const size_t i = sp->ring_cursor++;
+    if (i < ss->rings.size()) {
+        if (ss->ring_elems[i] != elems) return set_error(D2S_ERR_INVALID, "temporal stream state does not match the plan (ring %zu: %zu vs %zu elements)", i, ss->ring_elems[i], elems);
+        *p = ss->rings[i];
+        return D2S_OK;
+    }
+    void *q = nullptr;
+    D2S_CHECK_CUDA(cudaMalloc(&q, elems * sizeof(__half)));
+    D2S_CHECK_CUDA(cudaMemset(q, 0, elems * sizeof(__half)));
+    ss->rings.push_back((__half *)q); ss->ring_elems.push_back(elems); ss->bytes += elems * sizeof(__half);
+    *p = (__half *)q;
+    return D2S_OK;
+}
+
 static int add_gemm(ShapePlan *sp, const GemmPlan &gp) {
     sp->gemms.push_back(gp);
     const GemmPlan *p = &sp->gemms.back();
@@ -285,7 +226,7 @@ static int add_temporal(ShapePlan *sp, const TemporalW &t, const __half *x, __ha
     for (int a = 0; a < 2; ++a) {
         const TAttnW w = t.att[a];
         __half *ring;
-        TRY(plan_alloc(sp, &ring, (size_t)d * 32 * 2 * C));
+        TRY(state_ring(sp, &ring, (size_t)d * 32 * 2 * C));
         sp->ops.push_back([=](cudaStream_t st) { return layernorm_launch(hs, w.ln_w, w.ln_b, ln16, d, C, 1e-5f, 0, 0, st); });
         GemmEpi eq; eq.c16 = qkv16; eq.ldc = 3 * C;
         TRY(add_linear(sp, ln16, C, w.qkv_w, C, d, 3 * C, C, eq));
@@ -316,7 +257,13 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     sp->out_bytes = (size_t)B * H * W * out_es;
     uint8_t *in_stage, *out_stage;
     TRY(plan_alloc(sp, &in_stage, sp->in_bytes)); TRY(plan_alloc(sp, &out_stage, sp->out_bytes));
-    if (c.temporal) TRY(plan_alloc(sp, &sp->frame_counter, 1));
+    if (c.temporal) {
+        if (!sp->state->frame_counter) {
+            D2S_CHECK_CUDA(cudaMalloc((void **)&sp->state->frame_counter, sizeof(long long)));
+            D2S_CHECK_CUDA(cudaMemset(sp->state->frame_counter, 0, sizeof(long long)));
+        }
+        sp->frame_counter = sp->state->frame_counter;
+    }
     sp->in_stage = in_stage; sp->out_stage = out_stage;
 
     // ---------------- embeddings ----------------
@@ -479,7 +426,7 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     return D2S_OK;
 }
 
-static int run_ops(ShapePlan *sp, cudaStream_t st) {
+int engine_run_ops(ShapePlan *sp, cudaStream_t st) {
     // Programmatic dependent launch between the kernels of the plan (common.cuh; the GEMM and attention kernels release their
     // dependents when their main loop is over, so the next kernel's prologue runs under their epilogue).  Measured on B200:
     // +3.6 % frames/s with 8 frames in flight (1794 vs 1731), but +0.07 ms for one frame alone (1.48 vs 1.42 ms) — so it is on for
@@ -522,6 +469,7 @@ extern "C" int d2s_create(const void *weight_blob, size_t nbytes, const d2s_mode
     e->F = cfg->fusion; e->Fh = cfg->fusion / 2; e->Fhp = round_up(e->Fh, 64);
     const char *ng = getenv("D2S_NO_GRAPH");
     e->use_graph = !(ng && ng[0] == '1');
+    if (const char *mp = getenv("D2S_MAX_PLANS")) { int v = atoi(mp); if (v >= 1) e->max_plans = (size_t)v; }
     rc = upload_weights(e, weight_blob, nbytes);
     if (rc) { d2s_destroy(e); return rc; }
     *out = e;
@@ -533,29 +481,43 @@ extern "C" int d2s_destroy(d2s_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->plans.clear();
+    h->states.clear();
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return D2S_OK;
 }
 
-extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, void *depth_out, int out_dtype, int B, int H, int W,
-                         d2s_stream_t stream) {
-    D2S_REQUIRE(h && pixel_values && depth_out, "d2s_infer: null argument");
-    D2S_REQUIRE(B >= 1 && H >= 14 && W >= 14 && H % h->cfg.patch == 0 && W % h->cfg.patch == 0, "d2s_infer: input %dx%dx%d must be a multiple of the patch size", B, H, W);
+// Find or build the plan for (shape, dtypes, stream, policy).  Building is the only host-synchronous path (like the reference's
+// lazy engine build at depth.py:1842-1862): buffers, tensor maps, graph capture.  The cache is LRU-bounded (max_plans): the
+// least recently used plan is destroyed after a device synchronise; temporal stream states outlive their plans.
+int d2s::engine_plan(d2s_engine *h, int B, int H, int W, int in_dtype, int out_dtype, cudaStream_t st, ShapePlan **out) {
+    const d2s_model_config &c = h->cfg;
+    D2S_REQUIRE(B >= 1 && H >= 14 && W >= 14 && H % c.patch == 0 && W % c.patch == 0, "d2s_infer: input %dx%dx%d must be a multiple of the patch size", B, H, W);
     D2S_REQUIRE(in_dtype == D2S_F32 || in_dtype == D2S_F16, "d2s_infer: pixel_values dtype %d", in_dtype);
     D2S_REQUIRE(out_dtype == D2S_F32 || out_dtype == D2S_F16, "d2s_infer: output dtype %d", out_dtype);
-    D2S_REQUIRE(!h->cfg.temporal || B == 1, "d2s_infer: a temporal (Video-Depth-Anything) engine takes one frame per call (B=%d)", B);
-    cudaStream_t st = (cudaStream_t)stream;
-    // One plan (activation buffers + tensor maps + graph) per shape AND per stream: frames submitted on different streams
-    // run concurrently on disjoint buffers while sharing the (read-only) weights.
-    std::vector<long long> key = {B, H, W, in_dtype, out_dtype, (long long)(uintptr_t)stream, h->policy};
+    D2S_REQUIRE(!c.temporal || B == 1, "d2s_infer: a temporal (Video-Depth-Anything) engine takes one frame per call (B=%d)", B);
+    D2S_REQUIRE(c.max_batch <= 0 || B <= c.max_batch, "d2s_infer: batch %d exceeds the engine's max_batch %d", B, c.max_batch);
+    D2S_REQUIRE((c.max_h <= 0 || H <= c.max_h) && (c.max_w <= 0 || W <= c.max_w), "d2s_infer: input %dx%d exceeds the engine's max_h x max_w %dx%d", H, W, c.max_h, c.max_w);
+    std::vector<long long> key = {B, H, W, in_dtype, out_dtype, (long long)(uintptr_t)st, h->policy};
     std::unique_lock<std::mutex> lock(h->mu);
     auto it = h->plans.find(key);
     if (it == h->plans.end()) {
-        // first frame of this shape: allocate buffers, encode tensor maps, capture the graph (the only host-synchronous path,
-        // like the reference's lazy engine build at depth.py:1842-1862)
+        if (h->plans.size() >= h->max_plans) {
+            auto victim = h->plans.begin();
+            for (auto p = h->plans.begin(); p != h->plans.end(); ++p)
+                if (p->second->last_use < victim->second->last_use) victim = p;
+            D2S_CHECK_CUDA(cudaDeviceSynchronize());      // the victim may still be running on its stream
+            if (h->last == victim->second.get()) h->last = nullptr;
+            h->plans.erase(victim);
+        }
         std::unique_ptr<ShapePlan> sp(new ShapePlan());
         sp->B = B; sp->H = H; sp->W = W; sp->in_dtype = in_dtype; sp->out_dtype = out_dtype; sp->stream = st; sp->policy = h->policy;
+        if (c.temporal) {
+            std::vector<long long> skey = {(long long)(uintptr_t)st, H, W};
+            auto &slot = h->states[skey];
+            if (!slot) slot.reset(new StreamState());
+            sp->state = slot.get();
+        }
         gemm_set_plan_policy(h->policy);
         int rc = build_plan(h, sp.get());
         gemm_set_plan_policy(0);
@@ -564,7 +526,7 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
             cudaStream_t cs;
             D2S_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
             cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-            int orc = ce == cudaSuccess ? run_ops(sp.get(), cs) : D2S_ERR_CUDA;
+            int orc = ce == cudaSuccess ? engine_run_ops(sp.get(), cs) : D2S_ERR_CUDA;
             cudaError_t ee = cudaStreamEndCapture(cs, &sp->graph);
             cudaStreamDestroy(cs);
             if (ce != cudaSuccess || ee != cudaSuccess || orc) return orc ? orc : set_error(D2S_ERR_CUDA, "d2s_infer: graph capture failed: %s", cudaGetErrorString(ee != cudaSuccess ? ee : ce));
@@ -573,16 +535,32 @@ extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, v
         it = h->plans.emplace(key, std::move(sp)).first;
     }
     ShapePlan *sp = it->second.get();
+    sp->last_use = ++h->tick;
     h->last = sp;
-    lock.unlock();
-    D2S_CHECK_CUDA(cudaMemcpyAsync(sp->in_stage, pixel_values, sp->in_bytes, cudaMemcpyDeviceToDevice, st));
+    *out = sp;
+    return D2S_OK;
+}
+
+int d2s::engine_run_plan(ShapePlan *sp, cudaStream_t st) {
     if (sp->exec) {
         D2S_CHECK_CUDA(cudaGraphLaunch(sp->exec, st));
         g_launch_count.fetch_add((long long)sp->ops.size(), std::memory_order_relaxed);
-    } else {
-        int rc = run_ops(sp, st);
-        if (rc) return rc;
+        return D2S_OK;
     }
+    return engine_run_ops(sp, st);
+}
+
+extern "C" int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, void *depth_out, int out_dtype, int B, int H, int W,
+                         d2s_stream_t stream) {
+    D2S_REQUIRE(h && pixel_values && depth_out, "d2s_infer: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    // One plan (activation buffers + tensor maps + graph) per shape AND per stream: frames submitted on different streams
+    // run concurrently on disjoint buffers while sharing the (read-only) weights.
+    ShapePlan *sp = nullptr;
+    int rc = engine_plan(h, B, H, W, in_dtype, out_dtype, st, &sp);
+    if (rc) return rc;
+    D2S_CHECK_CUDA(cudaMemcpyAsync(sp->in_stage, pixel_values, sp->in_bytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = engine_run_plan(sp, st))) return rc;
     D2S_CHECK_CUDA(cudaMemcpyAsync(depth_out, sp->out_stage, sp->out_bytes, cudaMemcpyDeviceToDevice, st));
     return D2S_OK;
 }
@@ -597,14 +575,30 @@ extern "C" int d2s_set_policy(d2s_handle h, int policy) {
 extern "C" int d2s_reset_stream(d2s_handle h, d2s_stream_t stream) {
     D2S_REQUIRE(h != nullptr, "d2s_reset_stream: null handle");
     std::unique_lock<std::mutex> lock(h->mu);
-    for (auto &kv : h->plans)
-        if (kv.second->stream == (cudaStream_t)stream && kv.second->frame_counter)
+    for (auto &kv : h->states)
+        if (kv.first[0] == (long long)(uintptr_t)stream && kv.second->frame_counter)
             D2S_CHECK_CUDA(cudaMemsetAsync(kv.second->frame_counter, 0, sizeof(long long), (cudaStream_t)stream));
+    return D2S_OK;
+}
+
+extern "C" int d2s_release_stream(d2s_handle h, d2s_stream_t stream) {
+    D2S_REQUIRE(h != nullptr, "d2s_release_stream: null handle");
+    std::unique_lock<std::mutex> lock(h->mu);
+    D2S_CHECK_CUDA(cudaDeviceSynchronize());     // (the stream handle itself may already be destroyed: do not synchronise on it)
+    for (auto it = h->plans.begin(); it != h->plans.end();) {
+        if (it->second->stream == (cudaStream_t)stream) {
+            if (h->last == it->second.get()) h->last = nullptr;
+            it = h->plans.erase(it);
+        } else ++it;
+    }
+    for (auto it = h->states.begin(); it != h->states.end();)
+        it = it->first[0] == (long long)(uintptr_t)stream ? h->states.erase(it) : std::next(it);
     return D2S_OK;
 }
 
 extern "C" int d2s_debug_tap(d2s_handle h, const char *name, float *dst, size_t max_elems, size_t *n_elems, d2s_stream_t stream) {
     D2S_REQUIRE(h && name && n_elems, "d2s_debug_tap: null argument");
+    std::unique_lock<std::mutex> lock(h->mu);
     D2S_REQUIRE(h->last, "d2s_debug_tap: no inference has run yet");
     auto it = h->last->taps.find(name);
     if (it == h->last->taps.end()) return set_error(D2S_ERR_INVALID, "d2s_debug_tap: unknown tap '%s'", name);
@@ -619,6 +613,8 @@ extern "C" int d2s_debug_tap(d2s_handle h, const char *name, float *dst, size_t 
 extern "C" size_t d2s_workspace_bytes(d2s_handle h) {
     if (!h) return 0;
     size_t t = h->weight_bytes;
+    std::unique_lock<std::mutex> lock(h->mu);
     for (auto &kv : h->plans) t += kv.second->total_bytes;
+    for (auto &kv : h->states) t += kv.second->bytes;
     return t;
 }

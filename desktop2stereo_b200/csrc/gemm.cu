@@ -772,6 +772,7 @@ int gemm_plan_linear(GemmPlan *p, const __half *A, int lda, const __half *Bw, in
     if ((rc = tma_encode_2d(&p->tmA, A, M, K, lda, BM))) return rc;
     if ((rc = tma_encode_2d(&p->tmB, Bw, N, K, ldb, p->pair ? p->BN / 2 : p->BN))) return rc;
     p->grid = p->pair ? dim3((p->mtiles + 1) / 2 * 2, ceil_div(N, p->BN)) : dim3(ceil_div(N, p->BN), p->mtiles);
+    D2S_REQUIRE(p->grid.y <= 65535, "gemm: %d row tiles exceed the grid limit (M=%d): lower the batch", p->mtiles, M);
     finish_plan(p);
     return D2S_OK;
 }
@@ -793,6 +794,7 @@ int gemm_plan_conv3x3(GemmPlan *p, const __half *A, const ConvGeom &g, const __h
     if ((rc = encode_nhwc(&p->tmA, A, g, p->TW, p->TH))) return rc;
     if ((rc = tma_encode_2d(&p->tmB, Bw, N, p->K, p->K, p->pair ? p->BN / 2 : p->BN))) return rc;
     p->grid = p->pair ? dim3((p->mtiles + 1) / 2 * 2, ceil_div(N, p->BN)) : dim3(ceil_div(N, p->BN), p->mtiles);
+    D2S_REQUIRE(p->grid.y <= 65535, "conv: %d pixel tiles exceed the grid limit (%dx%dx%d): lower the batch", p->mtiles, g.B, g.H, g.W);
     finish_plan(p);
     return D2S_OK;
 }

@@ -1,0 +1,315 @@
+// The whole-frame pipeline: capture frame in -> packed stereo frame out, `slots` frames in flight, ONE C call per frame.
+//
+// This is the caller side of the hot path.  The reference runs capture -> process -> predict_depth -> make_sbs as
+// three Python threads joined by two size-1 queues (reference main.py:67-68, 232-262, 1336-1341): a 3-deep software pipeline in
+// which every frame costs ~15 framework calls.  Here each in-flight frame owns a slot: a CUDA stream, fixed device buffers (so
+// nothing is allocated per frame), pinned host buffers, the engine plan of that stream, and two CUDA graphs that replay the
+// frame's kernels:
+//     [H2D copy] -> process kernel -> graph A { resize+normalise -> network (~140 kernels) -> percentile bounds, point ops, blur-x }
+//                -> wait(previous frame's EMA) -> blur-y + DepthStabilizer EMA -> signal EMA
+//                -> graph B { depth upsample + stereo warp/pack }  -> [D2H copy] -> done
+// The EMA of DepthStabilizer (depth.py:1865-1887) is the only cross-frame dependency of the path; it is the single kernel between
+// the two graphs, ordered frame-to-frame with an event, so the networks of consecutive frames overlap freely.  The antialias
+// weight tables of both resizes are input-independent and are built once at creation (the per-call entry points rebuild them).
+// Arithmetic is that of d2s_process / d2s_preprocess / d2s_infer / d2s_postprocess / d2s_make_sbs — the same kernels, launched
+// through the same code — so a frame through the pipe equals the same frame through the five calls, bit for bit.
+#include <vector>
+
+#include "engine.cuh"
+#include "prepost.cuh"
+
+#define TRY_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+namespace d2s {
+
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr, ema_ev = nullptr, in_ev = nullptr, t[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *d_frame = nullptr;      // captured frame [h0,w0,ch] u8
+    void *d_rgb = nullptr;           // process() output [3,h,w] rgb_dtype
+    void *ws_proc = nullptr, *ws_pre = nullptr, *ws_post = nullptr;
+    void *d_depth = nullptr;         // [h,w] fp16: predict_depth's return value
+    void *d_out = nullptr;           // packed stereo frame
+    void *h_in = nullptr, *h_out = nullptr;
+    ShapePlan *plan = nullptr;
+    cudaGraphExec_t gA = nullptr, gB = nullptr;
+    cudaGraph_t graphA = nullptr, graphB = nullptr;
+    long long kernels_a = 0, kernels_b = 0;
+    bool busy = false, traced = false;
+};
+
+}  // namespace d2s
+
+struct d2s_pipe {
+    d2s_pipe_config cfg;
+    d2s_engine *engine;
+    int device;
+    int h, w;          // size of process()'s output (== frame size unless target_height < frame_h)
+    int Hm, Wm;        // model input
+    int oh, ow;        // packed stereo frame
+    size_t frame_bytes, out_bytes, rgb_es, out_es;
+    size_t ws_proc_bytes, ws_pre_bytes, ws_post_bytes;
+    void *ema_state = nullptr;               // [Hm,Wm] fp16, NaN = unset (d2s_post_params.ema_valid == 2)
+    cudaEvent_t last_ema = nullptr;          // EMA event of the most recently submitted frame
+    bool trace = false;
+    std::vector<d2s::PipeSlot> slots;
+};
+
+namespace d2s {
+
+static size_t dtype_size(int dt) { return dt == D2S_F32 ? 4 : (dt == D2S_U8 ? 1 : 2); }
+
+static void fill_post(const d2s_pipe *p, const PipeSlot &s, d2s_post_params *pp) {
+    const d2s_pipe_config &c = p->cfg;
+    *pp = d2s_post_params{};
+    pp->depth_in = s.plan->out_stage; pp->in_dtype = D2S_F16; pp->H = p->Hm; pp->W = p->Wm;
+    pp->out = s.d_depth; pp->out_dtype = D2S_F16; pp->out_h = p->h; pp->out_w = p->w;
+    pp->compute_dtype = D2S_F16;          // the reference's CUDA path post-processes the autocast (fp16) depth in fp16
+    pp->metric = c.metric; pp->percentile = c.percentile; pp->subsample_cap = c.subsample_cap; pp->gamma = c.gamma;
+    pp->foreground_scale = c.foreground_scale; pp->aa_strength = c.aa_strength;
+    pp->ema_state = c.use_temporal_smooth ? p->ema_state : nullptr; pp->ema_valid = 2; pp->ema_alpha = c.ema_alpha;
+    pp->workspace = s.ws_post; pp->workspace_bytes = p->ws_post_bytes;
+}
+
+static void fill_warp(const d2s_pipe *p, const PipeSlot &s, d2s_warp_params *wp) {
+    const d2s_pipe_config &c = p->cfg;
+    *wp = d2s_warp_params{};
+    wp->rgb.base = s.d_rgb; wp->rgb.dtype = c.rgb_dtype; wp->rgb.sc = (int64_t)p->h * p->w; wp->rgb.sy = p->w; wp->rgb.sx = 1;
+    wp->out.base = s.d_out; wp->out.dtype = c.out_dtype; wp->out.sc = 1; wp->out.sy = (int64_t)3 * p->ow; wp->out.sx = 3;
+    wp->depth = s.d_depth; wp->depth_dtype = D2S_F16; wp->depth_h = p->h; wp->depth_w = p->w; wp->h = p->h; wp->w = p->w;
+    wp->ipd_uv = c.ipd_uv; wp->depth_ratio = c.depth_ratio; wp->convergence = c.convergence;
+    wp->display_mode = c.display_mode; wp->fill_16_9 = c.fill_16_9; wp->warp_mode = D2S_WARP_BILINEAR;
+    wp->rgb_round_to_depth_dtype = c.rgb_dtype != D2S_F16;   // make_sbs casts rgb to depth.dtype (depth.py:2209-2215)
+}
+
+static int capture_begin(cudaStream_t st) {
+    D2S_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    return D2S_OK;
+}
+static int capture_end(cudaStream_t st, int rc, cudaGraph_t *g, cudaGraphExec_t *exec) {
+    cudaError_t ee = cudaStreamEndCapture(st, g);
+    if (rc) return rc;
+    if (ee != cudaSuccess) return set_error(D2S_ERR_CUDA, "d2s_pipe_create: graph capture failed: %s", cudaGetErrorString(ee));
+    D2S_CHECK_CUDA(cudaGraphInstantiate(exec, *g, 0));
+    return D2S_OK;
+}
+
+static int build_slot(d2s_pipe *p, PipeSlot &s) {
+    const d2s_pipe_config &c = p->cfg;
+    D2S_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.ema_ev, cudaEventDisableTiming));
+    D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.in_ev, cudaEventDisableTiming));
+    for (auto &e : s.t) D2S_CHECK_CUDA(cudaEventCreate(&e));
+    D2S_CHECK_CUDA(cudaMalloc((void **)&s.d_frame, p->frame_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.d_rgb, (size_t)3 * p->h * p->w * p->rgb_es));
+    if (p->ws_proc_bytes) D2S_CHECK_CUDA(cudaMalloc(&s.ws_proc, p->ws_proc_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.ws_pre, p->ws_pre_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.ws_post, p->ws_post_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.d_depth, (size_t)p->h * p->w * 2));
+    D2S_CHECK_CUDA(cudaMalloc(&s.d_out, p->out_bytes));
+    if (c.host_io) {
+        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_in, p->frame_bytes, cudaHostAllocDefault));
+        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_out, p->out_bytes, cudaHostAllocDefault));
+    }
+    TRY_RC(engine_plan(p->engine, 1, p->Hm, p->Wm, D2S_F16, D2S_F16, s.stream, &s.plan));
+
+    // input-independent tables of the two antialias resizes: once, here
+    d2s_image src{};
+    src.base = s.d_rgb; src.dtype = c.rgb_dtype; src.sc = (int64_t)p->h * p->w; src.sy = p->w; src.sx = 1;
+    TRY_RC(process_phases(s.d_frame, c.frame_h, c.frame_w, c.channels, s.d_rgb, c.rgb_dtype, p->h, p->w, s.ws_proc, p->ws_proc_bytes, 1, s.stream));
+    TRY_RC(preprocess_phases(&src, p->h, p->w, s.plan->in_stage, D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 1, s.stream));
+    D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
+
+    d2s_post_params pp; fill_post(p, s, &pp);
+    d2s_warp_params wp; fill_warp(p, s, &wp);
+    const bool split = c.use_temporal_smooth != 0;
+    // graph A
+    long long k0 = g_launch_count.load();
+    TRY_RC(capture_begin(s.stream));
+    int rc = preprocess_phases(&src, p->h, p->w, s.plan->in_stage, D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 2, s.stream);
+    if (!rc) rc = engine_run_ops(s.plan, s.stream);
+    if (!rc) rc = postprocess_phases(&pp, split ? POST_PHASE_HEAD : POST_PHASE_ALL, s.stream);
+    if (!rc && !split) rc = d2s_make_sbs(&wp, s.stream);
+    TRY_RC(capture_end(s.stream, rc, &s.graphA, &s.gA));
+    s.kernels_a = g_launch_count.load() - k0;
+    if (split) {
+        k0 = g_launch_count.load();
+        TRY_RC(capture_begin(s.stream));
+        rc = postprocess_phases(&pp, POST_PHASE_UP, s.stream);
+        if (!rc) rc = d2s_make_sbs(&wp, s.stream);
+        TRY_RC(capture_end(s.stream, rc, &s.graphB, &s.gB));
+        s.kernels_b = g_launch_count.load() - k0;
+    }
+    return D2S_OK;
+}
+
+static void free_slot(PipeSlot &s) {
+    if (s.gA) cudaGraphExecDestroy(s.gA);
+    if (s.gB) cudaGraphExecDestroy(s.gB);
+    if (s.graphA) cudaGraphDestroy(s.graphA);
+    if (s.graphB) cudaGraphDestroy(s.graphB);
+    for (void *q : {(void *)s.d_frame, s.d_rgb, s.ws_proc, s.ws_pre, s.ws_post, s.d_depth, s.d_out}) if (q) cudaFree(q);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    for (cudaEvent_t e : {s.done, s.ema_ev, s.in_ev, s.t[0], s.t[1], s.t[2], s.t[3]}) if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2s_pipe_handle *out) {
+    D2S_REQUIRE(engine && cfg && out, "d2s_pipe_create: null argument");
+    D2S_REQUIRE(cfg->frame_h > 0 && cfg->frame_w > 1 && (cfg->channels == 3 || cfg->channels == 4), "d2s_pipe_create: frame %dx%dx%d", cfg->frame_h, cfg->frame_w, cfg->channels);
+    D2S_REQUIRE(cfg->slots >= 1 && cfg->slots <= 64, "d2s_pipe_create: slots=%d (1..64)", cfg->slots);
+    D2S_REQUIRE(cfg->rgb_dtype == D2S_F16 || cfg->rgb_dtype == D2S_F32, "d2s_pipe_create: rgb_dtype %d (F16 or F32)", cfg->rgb_dtype);
+    D2S_REQUIRE(cfg->out_dtype == D2S_F32 || cfg->out_dtype == D2S_U8 || cfg->out_dtype == D2S_F16, "d2s_pipe_create: out_dtype %d", cfg->out_dtype);
+    D2S_REQUIRE(cfg->display_mode >= 0 && cfg->display_mode <= 3, "d2s_pipe_create: display_mode %d", cfg->display_mode);
+    D2S_REQUIRE(cfg->depth_resolution > 0 && cfg->patch == engine->cfg.patch, "d2s_pipe_create: depth_resolution %d / patch %d", cfg->depth_resolution, cfg->patch);
+    // a temporal engine keeps ONE video's window per stream: frames of that video cannot be spread over several slots
+    D2S_REQUIRE(!engine->cfg.temporal || cfg->slots == 1, "d2s_pipe_create: a temporal (Video-Depth-Anything) engine needs slots == 1 (its frames are sequential; run one pipe per video)");
+    D2S_CHECK_CUDA(cudaSetDevice(engine->device));
+    d2s_pipe *p = new d2s_pipe();
+    p->cfg = *cfg; p->engine = engine; p->device = engine->device;
+    if (cfg->target_height >= cfg->frame_h) { p->h = cfg->frame_h; p->w = cfg->frame_w; }
+    else {   // depth.py:555-559
+        p->h = (cfg->target_height / 2) * 2;
+        p->w = ((int)((double)cfg->frame_w * (double)cfg->target_height / (double)cfg->frame_h) / 2) * 2;
+    }
+    int rc = d2s_model_input_shape(p->h, p->w, cfg->depth_resolution, cfg->patch, &p->Hm, &p->Wm);
+    if (!rc) rc = d2s_sbs_out_shape(p->h, p->w, cfg->display_mode, cfg->fill_16_9, &p->oh, &p->ow);
+    if (rc || p->h < 1 || p->w < 2) { delete p; return rc ? rc : set_error(D2S_ERR_INVALID, "d2s_pipe_create: processed size %dx%d", p->h, p->w); }
+    p->rgb_es = dtype_size(cfg->rgb_dtype); p->out_es = dtype_size(cfg->out_dtype);
+    p->frame_bytes = (size_t)cfg->frame_h * cfg->frame_w * cfg->channels;
+    p->out_bytes = (size_t)p->oh * p->ow * 3 * p->out_es;
+    p->ws_proc_bytes = process_workspace_bytes(cfg->frame_h, cfg->frame_w, p->h, p->w);
+    p->ws_pre_bytes = d2s_preprocess_workspace_bytes(p->h, p->w, p->Hm, p->Wm);
+    p->ws_post_bytes = d2s_postprocess_workspace_bytes(p->Hm, p->Wm);
+    rc = [&]() -> int {
+        D2S_CHECK_CUDA(cudaMalloc(&p->ema_state, (size_t)p->Hm * p->Wm * 2));
+        D2S_CHECK_CUDA(cudaMemset(p->ema_state, 0xFF, (size_t)p->Hm * p->Wm * 2));
+        // several frames in flight share the GPU: the throughput tile policy (d2s_set_policy); one frame alone: latency
+        const int old_policy = engine->policy;
+        { std::unique_lock<std::mutex> lock(engine->mu); engine->policy = cfg->slots > 1 ? D2S_POLICY_THROUGHPUT : D2S_POLICY_LATENCY; }
+        p->slots.resize(cfg->slots);
+        int r = D2S_OK;
+        for (auto &s : p->slots)
+            if ((r = build_slot(p, s))) break;
+        { std::unique_lock<std::mutex> lock(engine->mu); engine->policy = old_policy; }
+        return r;
+    }();
+    if (rc) { d2s_pipe_destroy(p); return rc; }
+    *out = p;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_destroy(d2s_pipe_handle p) {
+    if (!p) return D2S_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (auto &s : p->slots) {
+        if (s.stream) d2s_release_stream(p->engine, s.stream);
+        free_slot(s);
+    }
+    if (p->ema_state) cudaFree(p->ema_state);
+    delete p;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_geometry(d2s_pipe_handle p, int *h, int *w, int *model_h, int *model_w, int *out_h, int *out_w, size_t *frame_bytes, size_t *out_bytes) {
+    D2S_REQUIRE(p != nullptr, "d2s_pipe_geometry: null pipe");
+    if (h) *h = p->h; if (w) *w = p->w; if (model_h) *model_h = p->Hm; if (model_w) *model_w = p->Wm;
+    if (out_h) *out_h = p->oh; if (out_w) *out_w = p->ow; if (frame_bytes) *frame_bytes = p->frame_bytes; if (out_bytes) *out_bytes = p->out_bytes;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_slot_buffers(d2s_pipe_handle p, int slot, void **host_in, void **host_out, void **dev_in, void **dev_out, void **dev_depth,
+                                     d2s_stream_t *stream) {
+    D2S_REQUIRE(p && slot >= 0 && slot < (int)p->slots.size(), "d2s_pipe_slot_buffers: bad slot");
+    const PipeSlot &s = p->slots[slot];
+    if (host_in) *host_in = s.h_in; if (host_out) *host_out = s.h_out; if (dev_in) *dev_in = s.d_frame; if (dev_out) *dev_out = s.d_out;
+    if (dev_depth) *dev_depth = s.d_depth; if (stream) *stream = s.stream;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d2s_stream_t frame_ready_on) {
+    D2S_REQUIRE(p && slot >= 0 && slot < (int)p->slots.size(), "d2s_pipe_submit: bad slot");
+    PipeSlot &s = p->slots[slot];
+    D2S_REQUIRE(!s.busy, "d2s_pipe_submit: slot %d still holds an uncollected frame (d2s_pipe_wait first)", slot);
+    const d2s_pipe_config &c = p->cfg;
+    cudaStream_t st = s.stream;
+    if (frame && !c.host_io && frame_ready_on != (d2s_stream_t)st) {   // a device frame produced on another stream
+        D2S_CHECK_CUDA(cudaEventRecord(s.in_ev, (cudaStream_t)frame_ready_on));
+        D2S_CHECK_CUDA(cudaStreamWaitEvent(st, s.in_ev, 0));
+    }
+    s.traced = p->trace;
+    if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[0], st));
+    const uint8_t *src;
+    if (c.host_io) {
+        D2S_CHECK_CUDA(cudaMemcpyAsync(s.d_frame, frame ? frame : s.h_in, p->frame_bytes, cudaMemcpyHostToDevice, st));
+        src = s.d_frame;
+    } else src = frame ? (const uint8_t *)frame : s.d_frame;
+    int rc = process_phases(src, c.frame_h, c.frame_w, c.channels, s.d_rgb, c.rgb_dtype, p->h, p->w, s.ws_proc, p->ws_proc_bytes, 2, st);
+    if (rc) return rc;
+    if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[1], st));
+    D2S_CHECK_CUDA(cudaGraphLaunch(s.gA, st));
+    long long kernels = s.kernels_a;
+    if (s.gB) {
+        if (p->last_ema && p->last_ema != s.ema_ev) D2S_CHECK_CUDA(cudaStreamWaitEvent(st, p->last_ema, 0));
+        d2s_post_params pp; fill_post(p, s, &pp);
+        if ((rc = postprocess_phases(&pp, POST_PHASE_EMA, st))) return rc;
+        D2S_CHECK_CUDA(cudaEventRecord(s.ema_ev, st));
+        p->last_ema = s.ema_ev;
+        if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[2], st));
+        D2S_CHECK_CUDA(cudaGraphLaunch(s.gB, st));
+        kernels += s.kernels_b;
+    }
+    g_launch_count.fetch_add(kernels, std::memory_order_relaxed);
+    if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[3], st));
+    if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, p->out_bytes, cudaMemcpyDeviceToHost, st));
+    D2S_CHECK_CUDA(cudaEventRecord(s.done, st));
+    s.busy = true;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_wait(d2s_pipe_handle p, int slot) {
+    D2S_REQUIRE(p && slot >= 0 && slot < (int)p->slots.size(), "d2s_pipe_wait: bad slot");
+    PipeSlot &s = p->slots[slot];
+    D2S_REQUIRE(s.busy, "d2s_pipe_wait: slot %d has no frame in flight", slot);
+    D2S_CHECK_CUDA(cudaEventSynchronize(s.done));
+    s.busy = false;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_set_trace(d2s_pipe_handle p, int on) {
+    D2S_REQUIRE(p != nullptr, "d2s_pipe_set_trace: null pipe");
+    p->trace = on != 0;
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_slot_times(d2s_pipe_handle p, int slot, float ms[3]) {
+    D2S_REQUIRE(p && ms && slot >= 0 && slot < (int)p->slots.size(), "d2s_pipe_slot_times: bad arguments");
+    PipeSlot &s = p->slots[slot];
+    D2S_REQUIRE(s.traced && !s.busy, "d2s_pipe_slot_times: slot %d was not traced, or is still in flight", slot);
+    D2S_CHECK_CUDA(cudaEventElapsedTime(&ms[0], s.t[0], s.t[1]));
+    if (s.gB) {
+        D2S_CHECK_CUDA(cudaEventElapsedTime(&ms[1], s.t[1], s.t[2]));
+        D2S_CHECK_CUDA(cudaEventElapsedTime(&ms[2], s.t[2], s.t[3]));
+    } else {
+        D2S_CHECK_CUDA(cudaEventElapsedTime(&ms[1], s.t[1], s.t[3]));
+        ms[2] = 0.f;
+    }
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_reset(d2s_pipe_handle p) {
+    D2S_REQUIRE(p != nullptr, "d2s_pipe_reset: null pipe");
+    for (auto &s : p->slots) D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
+    D2S_CHECK_CUDA(cudaMemset(p->ema_state, 0xFF, (size_t)p->Hm * p->Wm * 2));
+    p->last_ema = nullptr;
+    if (p->engine->cfg.temporal)
+        for (auto &s : p->slots) { int rc = d2s_reset_stream(p->engine, s.stream); if (rc) return rc; }
+    return D2S_OK;
+}

@@ -10,7 +10,7 @@
 // then the vertical one — evaluated in fp32.  Compiled with -fmad=false; FMAs are explicit.
 #include <math.h>
 
-#include "common.cuh"
+#include "prepost.cuh"
 
 namespace d2s {
 
@@ -161,17 +161,22 @@ static ResizePlan plan_resize(int h, int w, int oh, int ow, bool cubic) {
     return p;
 }
 
+// what: bit 0 = build the two weight tables (input-independent: a caller that keeps its workspace may do it once per shape),
+//       bit 1 = run the two filter passes
 template <bool CUBIC, bool NORM>
 static int run_resize(const d2s_image *src, int h, int w, void *dst, int dst_dtype, int oh, int ow, const float *mean,
-                      const float *std, void *ws, size_t ws_bytes, d2s_stream_t st) {
+                      const float *std, void *ws, size_t ws_bytes, d2s_stream_t st, int what = 3) {
     ResizePlan p = plan_resize(h, w, oh, ow, CUBIC);
     D2S_REQUIRE(ws && ws_bytes >= p.total, "resize: workspace too small (%zu < %zu)", ws_bytes, p.total);
     char *b = (char *)ws;
     AATable tw{(int *)(b + p.off_xmin_w), (int *)(b + p.off_xsize_w), (float *)(b + p.off_ww), p.Kw};
     AATable th{(int *)(b + p.off_xmin_h), (int *)(b + p.off_xsize_h), (float *)(b + p.off_wh), p.Kh};
     float *tmp = (float *)(b + p.off_tmp);
-    D2S_LAUNCH((aa_table_kernel<CUBIC>), ceil_div(ow, 128), 128, 0, st, tw, w, ow, p.scale_w, p.support_w);
-    D2S_LAUNCH((aa_table_kernel<CUBIC>), ceil_div(oh, 128), 128, 0, st, th, h, oh, p.scale_h, p.support_h);
+    if (what & 1) {
+        D2S_LAUNCH((aa_table_kernel<CUBIC>), ceil_div(ow, 128), 128, 0, st, tw, w, ow, p.scale_w, p.support_w);
+        D2S_LAUNCH((aa_table_kernel<CUBIC>), ceil_div(oh, 128), 128, 0, st, th, h, oh, p.scale_h, p.support_h);
+    }
+    if (!(what & 2)) { D2S_POST_LAUNCH(); return D2S_OK; }
     ImgView v{src->base, src->sc, src->sy, src->sx};
     dim3 gh(ceil_div(ow, 128), h);
     switch (src->dtype) {
@@ -317,7 +322,8 @@ __global__ void post_blur_kernel(const float *__restrict__ in, int H, int W, Blu
     size_t o = (size_t)y * W + x;
     if (AXIS == 1) {
         if (ema) {  // DepthStabilizer: prev.lerp_(depth, 1-alpha)  (Lerp.h: weight < 0.5 -> self + w*(end-self))
-            if (ema_valid) acc = round_to<CT>(__fmaf_rn(ema_w, __fsub_rn(acc, to_f32<CT>(ema[o])), to_f32<CT>(ema[o])));
+            const float prev = to_f32<CT>(ema[o]);
+            if (ema_valid == 1 || (ema_valid == 2 && prev == prev)) acc = round_to<CT>(__fmaf_rn(ema_w, __fsub_rn(acc, prev), prev));
             ema[o] = from_f32<CT>(acc);
         }
         if (out_low) out_low[o] = from_f32<CT>(acc);
@@ -333,7 +339,8 @@ __global__ void post_ema_kernel(float *__restrict__ buf, int n, CT *__restrict__
     if (i >= n) return;
     float acc = buf[i];
     if (ema) {
-        if (ema_valid) acc = round_to<CT>(__fmaf_rn(ema_w, __fsub_rn(acc, to_f32<CT>(ema[i])), to_f32<CT>(ema[i])));
+        const float prev = to_f32<CT>(ema[i]);
+        if (ema_valid == 1 || (ema_valid == 2 && prev == prev)) acc = round_to<CT>(__fmaf_rn(ema_w, __fsub_rn(acc, prev), prev));
         ema[i] = from_f32<CT>(acc);
     }
     if (out_low) out_low[i] = from_f32<CT>(acc);
@@ -390,8 +397,11 @@ static BlurW make_gauss(float strength) {
     return bw;
 }
 
+// phases: POST_PHASE_HEAD = percentile bounds + point ops + horizontal blur (no cross-frame state),
+//         POST_PHASE_EMA  = vertical blur + DepthStabilizer EMA + low-res store (the one cross-frame dependency of the path),
+//         POST_PHASE_UP   = final bilinear upsample
 template <typename IT, typename CT>
-static int run_post(const d2s_post_params *p, d2s_stream_t st) {
+static int run_post(const d2s_post_params *p, d2s_stream_t st, int phases) {
     const int H = p->H, W = p->W, n = H * W;
     size_t need = d2s_postprocess_workspace_bytes(H, W);
     D2S_REQUIRE(p->workspace && p->workspace_bytes >= need, "d2s_postprocess: workspace too small (%zu < %zu)", p->workspace_bytes, need);
@@ -404,10 +414,12 @@ static int run_post(const d2s_post_params *p, d2s_stream_t st) {
     double lo_q = fmax(0.0, fmin(1.0, (double)p->percentile / 100.0));
     int k = (int)nearbyint(lo_q * (double)(ns - 1)) + 1;
     k = k < 1 ? 1 : k; k = k > ns ? ns : k;
-    D2S_LAUNCH((post_bounds_kernel<IT, CT>), 1, 1024, 0, st, (const IT *)p->depth_in, n, step, ns, k, p->metric ? 1 : 0, p->subsample_cap, lo_q, bounds);
     int fg_on = fabs((double)p->foreground_scale) >= 1e-6;
     float fg_exp = (float)(1.0 / (1.0 + (double)p->foreground_scale));
-    D2S_LAUNCH((post_point_kernel<IT, CT>), ceil_div(n, 256), 256, 0, st, (const IT *)p->depth_in, n, bounds, p->gamma, fg_on, fg_exp, p->metric ? 1 : 0, bufA);
+    if (phases & POST_PHASE_HEAD) {
+        D2S_LAUNCH((post_bounds_kernel<IT, CT>), 1, 1024, 0, st, (const IT *)p->depth_in, n, step, ns, k, p->metric ? 1 : 0, p->subsample_cap, lo_q, bounds);
+        D2S_LAUNCH((post_point_kernel<IT, CT>), ceil_div(n, 256), 256, 0, st, (const IT *)p->depth_in, n, bounds, p->gamma, fg_on, fg_exp, p->metric ? 1 : 0, bufA);
+    }
     BlurW bw = make_gauss<CT>(p->aa_strength);
     D2S_REQUIRE(bw.k <= 63, "d2s_postprocess: anti-alias kernel size %d too large", bw.k);
     float ema_w = (float)(1.0 - (double)p->ema_alpha);
@@ -416,12 +428,12 @@ static int run_post(const d2s_post_params *p, d2s_stream_t st) {
     dim3 g(ceil_div(W, 128), H);
     float *res = bufA;
     if (bw.k >= 3) {
-        D2S_LAUNCH((post_blur_kernel<CT, 0>), g, 128, 0, st, bufA, H, W, bw, bufB, (CT *)nullptr, 0, 0.f, (CT *)nullptr);
-        D2S_LAUNCH((post_blur_kernel<CT, 1>), g, 128, 0, st, bufB, H, W, bw, bufA, ema, p->ema_valid, ema_w, out_low);
-    } else if (ema || out_low) {
+        if (phases & POST_PHASE_HEAD) D2S_LAUNCH((post_blur_kernel<CT, 0>), g, 128, 0, st, bufA, H, W, bw, bufB, (CT *)nullptr, 0, 0.f, (CT *)nullptr);
+        if (phases & POST_PHASE_EMA) D2S_LAUNCH((post_blur_kernel<CT, 1>), g, 128, 0, st, bufB, H, W, bw, bufA, ema, p->ema_valid, ema_w, out_low);
+    } else if ((ema || out_low) && (phases & POST_PHASE_EMA)) {
         D2S_LAUNCH((post_ema_kernel<CT>), ceil_div(n, 256), 256, 0, st, bufA, n, ema, p->ema_valid, ema_w, out_low);
     }
-    if (p->out) {
+    if (p->out && (phases & POST_PHASE_UP)) {
         dim3 gu(ceil_div(p->out_w, 128), p->out_h);
         float sh = (float)H / (float)p->out_h, sw = (float)W / (float)p->out_w;
         switch (p->out_dtype) {
@@ -436,11 +448,11 @@ static int run_post(const d2s_post_params *p, d2s_stream_t st) {
 }
 
 template <typename IT>
-static int run_post_ct(const d2s_post_params *p, d2s_stream_t st) {
+static int run_post_ct(const d2s_post_params *p, d2s_stream_t st, int phases) {
     switch (p->compute_dtype) {
-        case D2S_F32: return run_post<IT, float>(p, st);
-        case D2S_F16: return run_post<IT, __half>(p, st);
-        case D2S_BF16: return run_post<IT, __nv_bfloat16>(p, st);
+        case D2S_F32: return run_post<IT, float>(p, st, phases);
+        case D2S_F16: return run_post<IT, __half>(p, st, phases);
+        case D2S_BF16: return run_post<IT, __nv_bfloat16>(p, st, phases);
         default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: compute dtype %d", p->compute_dtype);
     }
 }
@@ -471,9 +483,25 @@ extern "C" size_t d2s_preprocess_workspace_bytes(int h, int w, int new_h, int ne
 extern "C" int d2s_preprocess(const d2s_image *src, int h, int w, void *dst, int dst_dtype, int new_h, int new_w,
                               const float mean[3], const float std[3], void *workspace, size_t workspace_bytes,
                               d2s_stream_t stream) {
-    D2S_REQUIRE(src && src->base && dst && h > 0 && w > 0 && new_h > 0 && new_w > 0, "d2s_preprocess: bad arguments");
+    return d2s::preprocess_phases(src, h, w, dst, dst_dtype, new_h, new_w, mean, std, workspace, workspace_bytes, 3, stream);
+}
+
+int d2s::preprocess_phases(const d2s_image *src, int h, int w, void *dst, int dst_dtype, int new_h, int new_w, const float mean[3],
+                           const float std[3], void *workspace, size_t workspace_bytes, int what, d2s_stream_t stream) {
+    D2S_REQUIRE(src && (src->base || !(what & 2)) && (dst || !(what & 2)) && h > 0 && w > 0 && new_h > 0 && new_w > 0, "d2s_preprocess: bad arguments");
     D2S_REQUIRE(mean && std, "d2s_preprocess: mean/std required");
-    return run_resize<true, true>(src, h, w, dst, dst_dtype, new_h, new_w, mean, std, workspace, workspace_bytes, stream);
+    return run_resize<true, true>(src, h, w, dst, dst_dtype, new_h, new_w, mean, std, workspace, workspace_bytes, stream, what);
+}
+
+size_t d2s::process_workspace_bytes(int h0, int w0, int h, int w) { return (h == h0 && w == w0) ? 0 : plan_resize(h0, w0, h, w, false).total; }
+
+// process() with a caller-owned workspace (no stream-ordered allocation: capturable, and the tables can be built once)
+int d2s::process_phases(const uint8_t *frame, int h0, int w0, int channels, void *out, int out_dtype, int h, int w, void *ws, size_t ws_bytes,
+                        int what, d2s_stream_t stream) {
+    if (h == h0 && w == w0) return (what & 2) ? d2s_process(frame, h0, w0, channels, out, out_dtype, h, w, stream) : D2S_OK;
+    d2s_image src{};
+    src.base = (void *)(frame + 2); src.dtype = D2S_U8; src.sc = -1; src.sy = (int64_t)w0 * channels; src.sx = channels;
+    return run_resize<false, false>(&src, h0, w0, out, out_dtype, h, w, nullptr, nullptr, ws, ws_bytes, stream, what);
 }
 
 extern "C" int d2s_process(const uint8_t *frame, int h0, int w0, int channels, void *out, int out_dtype, int h, int w,
@@ -508,15 +536,18 @@ extern "C" size_t d2s_postprocess_workspace_bytes(int H, int W) {
     return sizeof(float) * (64 + 2 * align_up((size_t)H * W, 64));
 }
 
-extern "C" int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream) {
+extern "C" int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream) { return d2s::postprocess_phases(p, POST_PHASE_ALL, stream); }
+
+int d2s::postprocess_phases(const d2s_post_params *p, int phases, d2s_stream_t stream) {
     D2S_REQUIRE(p && p->depth_in && p->H > 0 && p->W > 0, "d2s_postprocess: bad arguments");
+    D2S_REQUIRE(p->ema_valid >= 0 && p->ema_valid <= 2, "d2s_postprocess: ema_valid %d", p->ema_valid);
     D2S_REQUIRE(p->out == nullptr || (p->out_h > 0 && p->out_w > 0), "d2s_postprocess: bad output size");
     D2S_REQUIRE(p->subsample_cap >= 1, "d2s_postprocess: subsample_cap");
     D2S_REQUIRE(!p->metric || p->subsample_cap <= 8192, "d2s_postprocess: subsample_cap %d exceeds the sort capacity", p->subsample_cap);
     switch (p->in_dtype) {
-        case D2S_F32: return run_post_ct<float>(p, stream);
-        case D2S_F16: return run_post_ct<__half>(p, stream);
-        case D2S_BF16: return run_post_ct<__nv_bfloat16>(p, stream);
+        case D2S_F32: return run_post_ct<float>(p, stream, phases);
+        case D2S_F16: return run_post_ct<__half>(p, stream, phases);
+        case D2S_BF16: return run_post_ct<__nv_bfloat16>(p, stream, phases);
         default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_postprocess: in dtype %d", p->in_dtype);
     }
 }

@@ -112,13 +112,33 @@ def predict_depth(image_rgb, return_tuple=False, use_temporal_smooth: bool = Tru
     return depth
 
 
-def install(ref_depth_module, hf_model=None, **overrides):
-    """Patch an imported reference `depth` module so that main.py keeps calling its own names but lands on the B200
-    path: the engine goes into the wrapper slot exactly like TensorRTEngine would (depth.py:1597-1631), and the
-    module-level functions are replaced by the ones above."""
-    w = init(hf_model if hf_model is not None else ref_depth_module.model_wraper.model, **overrides)
+_REF_SETTINGS = {"depth_resolution": "DEPTH_RESOLUTION", "fp16": "FP16", "foreground_scale": "FOREGROUND_SCALE", "aa_strength": "AA_STRENGTH"}
+_PATCHED = ("process", "predict_depth", "make_sbs", "make_sbs_core")
+
+
+def install(ref_depth_module, hf_model=None, *, engine: B200Engine | None = None, device=None, **overrides):
+    """Patch an imported reference `depth` module so that main.py keeps calling its own names but lands on the B200 path:
+    the engine goes into the wrapper slot exactly like TensorRTEngine would (depth.py:1597-1631), and the module-level
+    `process`, `predict_depth`, `make_sbs`, `make_sbs_core` are replaced by the functions above.
+
+    Call it once the reference module has executed COMPLETELY — as the last statement of depth.py (after make_sbs, :2231) or
+    from main.py right after `import depth` and before `from depth import process, predict_depth` (main.py:44): the reference
+    defines predict_depth (:1897), make_sbs_core (:2122) and make_sbs (:2186) below the place where it creates `model_wraper`
+    (:1784), so a call placed there would be overwritten by those definitions.
+    Settings the reference module holds as constants (DEPTH_RESOLUTION, FP16, FOREGROUND_SCALE, AA_STRENGTH; utils.py:819-907)
+    are taken from it unless overridden."""
+    missing = [n for n in _PATCHED if not hasattr(ref_depth_module, n)]
+    if missing:
+        raise _lib.D2SError(f"install(): {ref_depth_module.__name__} does not define {missing} (yet): call install() after the "
+                            "reference module has executed completely")
+    for key, const in _REF_SETTINGS.items():
+        if key not in overrides and hasattr(ref_depth_module, const):
+            overrides[key] = getattr(ref_depth_module, const)
+    if hf_model is None and engine is None:
+        hf_model = ref_depth_module.model_wraper.model
+    w = init(hf_model, engine=engine, device=device, **overrides)
     ref_depth_module.model_wraper.model = w.model
     ref_depth_module.model_wraper.backend = w.backend
-    for name in ("process", "predict_depth", "make_sbs", "make_sbs_core"):
+    for name in _PATCHED:
         setattr(ref_depth_module, name, globals()[name])
     return w

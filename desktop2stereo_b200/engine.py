@@ -81,6 +81,13 @@ class B200Engine:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().d2s_reset_stream(self._h, _stream_ptr(self.device)), "d2s_reset_stream")
 
+    def release_stream(self, stream=None):
+        """Free the plans (and, for temporal engines, the video state) the engine keeps for a CUDA stream — call it before the
+        stream is destroyed.  Host-synchronous."""
+        ptr = (stream.cuda_stream if stream is not None else _stream_ptr(self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().d2s_release_stream(self._h, ptr), "d2s_release_stream")
+
     def tap(self, name: str) -> torch.Tensor:
         """Debug/parity tap: an internal activation of the last inference, as a flat fp32 tensor."""
         n = C.c_size_t()

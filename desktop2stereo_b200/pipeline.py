@@ -1,141 +1,243 @@
-"""StereoPipeline — the caller side of the hot path: `depth` frames in flight over `depth` CUDA streams.
+"""StereoPipeline — the caller side of the hot path: `depth_slots` frames in flight, one C call per frame.
 
 The reference's main.py runs capture -> depth -> warp as three threads joined by size-1 queues (main.py:67-68, 232-262,
-1336-1341), i.e. a 3-deep software pipeline.  This class is the same idea on one GPU: each in-flight frame owns a CUDA
-stream, a pinned host staging buffer for the captured BGRA frame, a pinned host buffer for the SBS result and (inside the
-engine) its own activation buffers + CUDA graph, so H2D copy, network, warp and D2H copy of consecutive frames overlap.
-Per frame it issues exactly the reference-facing calls: process -> predict_depth -> make_sbs_core (+ the host copy that
-make_sbs does).  The only cross-frame dependency, the EMA of DepthStabilizer, is ordered with an event (prepost.py).
+1336-1341), i.e. a 3-deep software pipeline that issues ~15 framework calls per frame.  This class is a thin host-side
+handle on `d2s_pipe_*` (csrc/pipe.cu): each in-flight frame owns a slot (CUDA stream, fixed device buffers, pinned host
+buffers, CUDA graphs of the frame's kernels), so H2D copy, network, warp and D2H copy of consecutive frames overlap and the
+host does one ctypes call per frame.  Per frame it computes exactly what the reference-facing calls compute:
+process -> predict_depth -> make_sbs (+ the host copy make_sbs does) — same kernels, bit-identical results.  The only
+cross-frame dependency, the EMA of DepthStabilizer (depth.py:1865-1887), is ordered frame-to-frame inside the pipe.
 """
 from __future__ import annotations
 
+import ctypes as C
 from collections import deque
 
 import numpy as np
 import torch
 
+from . import _lib
 from . import depth as d2s_depth
-from .stereo import make_sbs_core, sbs_out_shape
+from ._lib import DISPLAY_MODES, PipeConfig
+from .prepost import IMAGENET_MEAN, IMAGENET_STD
+from .stereo import _TORCH2D2S, sbs_out_shape
+
+_NP_OF = {torch.float32: np.float32, torch.uint8: np.uint8, torch.float16: np.float16}
 
 
-class _Slot:
-    def __init__(self, device):
-        self.stream = torch.cuda.Stream(device)
-        self.h_in = None       # pinned BGRA frame
-        self.h_out = None      # pinned SBS result
-        self.done = torch.cuda.Event()
-        self.busy = False
-        self.dev_out = None
+class _Ticket:
+    __slots__ = ("pipe", "slot", "keep")
+
+    def __init__(self, pipe, slot, keep=None):
+        self.pipe, self.slot, self.keep = pipe, slot, keep
+
+
+class _Pipe:
+    """One d2s_pipe: fixed frame geometry and I/O mode."""
+
+    def __init__(self, owner: "StereoPipeline", h0: int, w0: int, ch: int, host_io: bool):
+        L = _lib.lib()
+        s = d2s_depth.settings
+        engine = d2s_depth.model_wraper.model
+        c = PipeConfig()
+        c.frame_h, c.frame_w, c.channels, c.target_height = h0, w0, ch, owner.target_height or h0
+        c.rgb_dtype = _TORCH2D2S[d2s_depth.DTYPE]
+        c.depth_resolution, c.patch = s.depth_resolution, s.patch
+        c.mean[:], c.std[:] = IMAGENET_MEAN, IMAGENET_STD
+        post = d2s_depth.depth_stabilizer
+        c.metric, c.percentile, c.subsample_cap, c.gamma = int(post.metric), post.percentile, post.subsample_cap, post.gamma
+        c.foreground_scale, c.aa_strength = post.foreground_scale, post.aa_strength
+        c.use_temporal_smooth, c.ema_alpha = int(owner.use_temporal_smooth), post.ema_alpha
+        p = owner.params
+        c.ipd_uv, c.depth_ratio, c.convergence = float(p["ipd_uv"]), float(p["depth_ratio"]), float(p["convergence"])
+        c.display_mode, c.fill_16_9 = DISPLAY_MODES[p["display_mode"]], int(bool(p["fill_16_9"]))
+        c.out_dtype, c.slots, c.host_io = _TORCH2D2S[owner.out_dtype], owner.n_slots, int(host_io)
+        self.handle = C.c_void_p()
+        self.device, self.host_io, self.L = owner.device, host_io, L
+        with torch.cuda.device(self.device):
+            _lib.check(L.d2s_pipe_create(engine._h, C.byref(c), C.byref(self.handle)), "d2s_pipe_create")
+        g = [C.c_int() for _ in range(6)]
+        fb, ob = C.c_size_t(), C.c_size_t()
+        _lib.check(L.d2s_pipe_geometry(self.handle, *[C.byref(x) for x in g], C.byref(fb), C.byref(ob)), "d2s_pipe_geometry")
+        self.h, self.w, self.Hm, self.Wm, self.oh, self.ow = [x.value for x in g]
+        self.frame_shape = (h0, w0, ch)
+        self.host_in, self.host_out, self.dev_out, self.dev_depth, self.streams = [], [], [], [], []
+        odt = owner.out_dtype
+        for i in range(owner.n_slots):
+            ptr = [C.c_void_p() for _ in range(6)]
+            _lib.check(L.d2s_pipe_slot_buffers(self.handle, i, *[C.byref(x) for x in ptr]), "d2s_pipe_slot_buffers")
+            hin, hout, _din, dout, ddep, st = [x.value for x in ptr]
+            if host_io:   # numpy views of the library's pinned buffers (no copy)
+                self.host_in.append(np.ctypeslib.as_array((C.c_uint8 * fb.value).from_address(hin)).reshape(h0, w0, ch))
+                raw = np.ctypeslib.as_array((C.c_uint8 * ob.value).from_address(hout))
+                self.host_out.append(raw.view(_NP_OF[odt]).reshape(self.oh, self.ow, 3))
+            self.dev_out.append(_device_view(dout, (self.oh, self.ow, 3), odt, self.device))
+            self.dev_depth.append(_device_view(ddep, (self.h, self.w), torch.float16, self.device))
+            self.streams.append(st)
+
+    def close(self):
+        if self.handle:
+            self.host_in, self.host_out, self.dev_out, self.dev_depth, self.streams = [], [], [], [], []
+            self.L.d2s_pipe_destroy(self.handle)
+            self.handle = None
+
+
+class _DevMem:
+    """__cuda_array_interface__ holder: lets torch view memory the library owns (a pipe slot's device buffers)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def _device_view(ptr, shape, dtype, device):
+    typestr = {torch.float32: "<f4", torch.float16: "<f2", torch.uint8: "|u1"}[dtype]
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DevMem(ptr, shape, typestr), device=device)
 
 
 class StereoPipeline:
     def __init__(self, depth_slots: int = 3, display_mode="Full-SBS", ipd_uv=0.064, depth_ratio=2.0, convergence=0.0,
-                 fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None):
-        """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and EMA state live there)."""
+                 fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None):
+        """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and the post-process settings live there).
+        A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224)."""
         d2s_depth._need_init()
+        engine = d2s_depth.model_wraper.model
+        if getattr(engine.cfg, "temporal", 0) and depth_slots != 1:
+            raise _lib.D2SError("a Video-Depth-Anything engine keeps one video's 32-frame window per CUDA stream: frames of one "
+                                "video are sequential, use depth_slots=1 (and one StereoPipeline per video)")
+        if display_mode not in DISPLAY_MODES:
+            raise ValueError(f"display_mode {display_mode!r}")
         self.device = d2s_depth.model_wraper.device if device is None else torch.device(device)
-        self.slots = [_Slot(self.device) for _ in range(depth_slots)]
+        self.n_slots = depth_slots
         self.params = dict(ipd_uv=ipd_uv, depth_ratio=depth_ratio, convergence=convergence, fill_16_9=fill_16_9,
                            display_mode=display_mode)
-        self.use_temporal_smooth, self.out_dtype = use_temporal_smooth, out_dtype
+        self.use_temporal_smooth, self.out_dtype, self.target_height = use_temporal_smooth, out_dtype, target_height
+        self._pipes: dict = {}
+        self._busy = [None] * depth_slots      # slot -> the _Pipe whose frame occupies it
         self.next = 0
         self.pending: deque = deque()
-        self.trace = None      # set to a list to collect per-frame CUDA events (start, after process, after depth, after warp)
+        self.trace = None      # set to a list to collect per-frame stage times (ms): process | network+post | upsample+warp
+
+    # ---- plumbing ----
+    def _pipe(self, shape, host_io) -> _Pipe:
+        key = (tuple(shape), bool(host_io))
+        p = self._pipes.get(key)
+        if p is None:
+            if len(shape) != 3 or shape[2] not in (3, 4):
+                raise ValueError(f"expected a uint8 [h,w,3|4] frame, got shape {tuple(shape)}")
+            p = self._pipes[key] = _Pipe(self, shape[0], shape[1], shape[2], host_io)
+        return p
+
+    def _acquire(self) -> int:
+        i = self.next
+        if self._busy[i] is not None:
+            raise RuntimeError("pipeline full: collect a result before submitting another frame")
+        self.next = (self.next + 1) % self.n_slots
+        return i
+
+    def _submit(self, pipe: _Pipe, slot: int, ptr, ready_stream, keep=None):
+        L = pipe.L
+        if (self.trace is not None) != getattr(pipe, "_tracing", False):
+            pipe._tracing = self.trace is not None
+            _lib.check(L.d2s_pipe_set_trace(pipe.handle, int(pipe._tracing)), "d2s_pipe_set_trace")
+        with torch.cuda.device(self.device):
+            _lib.check(L.d2s_pipe_submit(pipe.handle, slot, ptr, ready_stream), "d2s_pipe_submit")
+        self._busy[slot] = pipe
+        t = _Ticket(pipe, slot, keep)
+        self.pending.append(t)
+        return t
 
     # ---- submission ----
-    def _acquire(self) -> _Slot:
-        s = self.slots[self.next]
-        self.next = (self.next + 1) % len(self.slots)
-        if s.busy:
-            raise RuntimeError("pipeline full: collect a result before submitting another frame")
-        s.busy = True
-        return s
-
-    def _enqueue(self, s: _Slot, frame_dev: torch.Tensor, to_host: bool):
-        h = frame_dev.shape[0]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.trace is not None else None
-        if ev: ev[0].record(s.stream)
-        rgb = d2s_depth.process(frame_dev, h)
-        if ev: ev[1].record(s.stream)
-        engine = d2s_depth.model_wraper.model
-        prev = getattr(engine, "policy", None)
-        if prev is not None and len(self.slots) > 1:
-            engine.set_policy("throughput")        # several frames share the GPU: fewer, wider GEMM tiles
-        try:
-            depth = d2s_depth.predict_depth(rgb, use_temporal_smooth=self.use_temporal_smooth)
-        finally:
-            if prev is not None and len(self.slots) > 1:
-                engine.set_policy(prev)
-        if ev: ev[2].record(s.stream)
-        sbs = make_sbs_core(rgb, depth, out_layout="HWC", out_dtype=self.out_dtype, **self.params)
-        if ev:
-            ev[3].record(s.stream)
-            self.trace.append(ev)
-        if to_host:
-            if s.h_out is None or s.h_out.shape != sbs.shape or s.h_out.dtype != sbs.dtype:
-                s.h_out = torch.empty(sbs.shape, dtype=sbs.dtype, pin_memory=True)
-            s.h_out.copy_(sbs, non_blocking=True)
-        s.dev_out = sbs
-        s.done.record(s.stream)
-
     def submit(self, frame_bgra: np.ndarray):
-        """Host frame (BGRA/BGR u8 HWC ndarray) -> ticket.  Copies the frame into this slot's pinned buffer, then enqueues
-        H2D + process + predict_depth + make_sbs + D2H on the slot's stream; returns immediately."""
-        s = self._acquire()
-        src = torch.from_numpy(frame_bgra)
-        if s.h_in is None or s.h_in.shape != src.shape:
-            s.h_in = torch.empty(src.shape, dtype=torch.uint8, pin_memory=True)
-        s.h_in.copy_(src)                                   # capture buffer -> pinned staging (host memcpy)
-        with torch.cuda.stream(s.stream):
-            frame_dev = s.h_in.to(self.device, non_blocking=True)
-            self._enqueue(s, frame_dev, to_host=True)
-        self.pending.append(s)
-        return s
+        """Host frame (BGRA/BGR u8 HWC ndarray) -> ticket.  Copies the frame into the slot's pinned buffer (the capture ->
+        staging memcpy), then enqueues H2D + process + predict_depth + make_sbs + D2H on the slot's stream; returns immediately."""
+        if frame_bgra.dtype != np.uint8:
+            raise ValueError(f"expected a uint8 frame, got {frame_bgra.dtype}")
+        pipe = self._pipe(frame_bgra.shape, True)
+        slot = self._acquire()
+        np.copyto(pipe.host_in[slot], frame_bgra)
+        return self._submit(pipe, slot, None, None)
 
     def submit_pinned(self, frame_pinned: torch.Tensor):
-        """Same, for a frame that already sits in pinned host memory (zero host-side copy)."""
-        s = self._acquire()
-        with torch.cuda.stream(s.stream):
-            frame_dev = frame_pinned.to(self.device, non_blocking=True)
-            self._enqueue(s, frame_dev, to_host=True)
-        self.pending.append(s)
-        return s
+        """Same, for a frame that already sits in pinned host memory (no host-side copy).  The tensor must stay alive and
+        unchanged until the frame's result has been collected."""
+        if not frame_pinned.is_pinned() or frame_pinned.dtype != torch.uint8 or not frame_pinned.is_contiguous():
+            raise ValueError("submit_pinned needs a contiguous uint8 tensor in pinned host memory")
+        pipe = self._pipe(frame_pinned.shape, True)
+        slot = self._acquire()
+        return self._submit(pipe, slot, frame_pinned.data_ptr(), None, keep=frame_pinned)
 
     def submit_device(self, frame_dev: torch.Tensor):
-        """Frame already resident in HBM; the result stays on the device."""
-        s = self._acquire()
-        s.stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s.stream):
-            self._enqueue(s, frame_dev, to_host=False)
-        self.pending.append(s)
-        return s
+        """Frame already resident in HBM (produced on torch's current stream); the result stays on the device."""
+        if not frame_dev.is_cuda or frame_dev.dtype != torch.uint8 or not frame_dev.is_contiguous():
+            raise _lib.D2SError("submit_device needs a contiguous uint8 CUDA tensor (there is no CPU path)")
+        pipe = self._pipe(frame_dev.shape, False)
+        slot = self._acquire()
+        cur = torch.cuda.current_stream(self.device)
+        # the ticket keeps the tensor alive until the frame has been collected, so the caching allocator cannot hand its memory to
+        # someone else while the slot's stream still reads it (record_stream() on a library-owned stream would leave the allocator
+        # holding a stream handle that the pipe destroys)
+        return self._submit(pipe, slot, frame_dev.data_ptr(), cur.cuda_stream, keep=frame_dev)
 
     # ---- collection ----
-    def result(self, ticket: _Slot | None = None, host: bool = True):
-        """Blocks until the oldest (or the given) frame is complete; returns the float32 HWC ndarray (a view of the slot's
-        pinned buffer, valid until the slot is reused `depth_slots` submissions later) or the device tensor."""
-        s = ticket if ticket is not None else self.pending[0]
-        s.done.synchronize()
-        self.pending.remove(s)
-        s.busy = False
-        return s.h_out.numpy() if host else s.dev_out
+    def result(self, ticket: _Ticket | None = None, host: bool = True):
+        """Blocks until the oldest (or the given) frame is complete; returns the HWC ndarray (a view of the slot's pinned
+        buffer, valid until the slot is reused `depth_slots` submissions later) or the device tensor (same lifetime)."""
+        t = ticket if ticket is not None else self.pending[0]
+        pipe, slot = t.pipe, t.slot
+        _lib.check(pipe.L.d2s_pipe_wait(pipe.handle, slot), "d2s_pipe_wait")
+        self.pending.remove(t)
+        self._busy[slot] = None
+        t.keep = None
+        if self.trace is not None and getattr(pipe, "_tracing", False):
+            ms = (C.c_float * 3)()
+            _lib.check(pipe.L.d2s_pipe_slot_times(pipe.handle, slot, ms), "d2s_pipe_slot_times")
+            self.trace.append(tuple(ms))
+        if host and pipe.host_io:
+            return pipe.host_out[slot]
+        return pipe.dev_out[slot]
+
+    def depth_of(self, ticket: _Ticket) -> torch.Tensor:
+        """The [h,w] fp16 depth map (what predict_depth returns) of a collected frame; valid until the slot is reused."""
+        return ticket.pipe.dev_depth[ticket.slot]
 
     def run(self, frames, host: bool = True):
         """Generator: keeps the pipeline full while iterating `frames`; yields results in order."""
         def submit(f):
             if not host:
                 return self.submit_device(f)
-            if isinstance(f, torch.Tensor) and f.is_pinned():
-                return self.submit_pinned(f)          # already in pinned host memory: no staging copy on the host
+            if isinstance(f, torch.Tensor):
+                if f.is_pinned():
+                    return self.submit_pinned(f)      # already in pinned host memory: no staging copy on the host
+                f = f.numpy()
             return self.submit(f)
         for f in frames:
-            if len(self.pending) == len(self.slots):
+            if len(self.pending) == self.n_slots:
                 yield self.result(host=host)
             submit(f)
         while self.pending:
             yield self.result(host=host)
 
+    def reset(self):
+        """A new video: forget the EMA state (and a temporal engine's window)."""
+        while self.pending:
+            self.result()
+        for p in self._pipes.values():
+            _lib.check(p.L.d2s_pipe_reset(p.handle), "d2s_pipe_reset")
+
     def out_shape(self, h, w):
         oh, ow = sbs_out_shape(h, w, self.params["display_mode"], self.params["fill_16_9"])
         return oh, ow, 3
 
+    def close(self):
+        while self.pending:
+            self.result()
+        for p in self._pipes.values():
+            p.close()
+        self._pipes = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -121,6 +121,10 @@ class PostProcessor:
         cur = torch.cuda.current_stream(dev)
         if use_temporal_smooth:
             if self.prev is None or self.prev.shape != (H, W) or self.prev.device != dev or self.prev.dtype != cdt:
+                # (DepthStabilizer resets on a shape/device change, depth.py:1878-1882.)  Earlier frames may still be updating
+                # the old state on other streams: let them finish before its memory goes back to the allocator
+                if getattr(self, "_ema_event", None) is not None:
+                    self._ema_event.synchronize()
                 self.prev, self.prev_valid = torch.empty((H, W), dtype=cdt, device=dev), False
                 self._ema_event = None
             p.ema_state, p.ema_valid, p.ema_alpha = self.prev.data_ptr(), int(self.prev_valid), self.ema_alpha

@@ -25,7 +25,7 @@ import numpy as np
 from ._lib import ModelConfig
 
 
-def config_from_hf(hf_config, max_batch=1, max_h=518, max_w=518) -> ModelConfig:
+def config_from_hf(hf_config, max_batch=0, max_h=0, max_w=0) -> ModelConfig:
     b = hf_config.backbone_config
     c = ModelConfig()
     c.hidden, c.layers, c.heads = b.hidden_size, b.num_hidden_layers, b.num_attention_heads
@@ -103,7 +103,7 @@ VDA_ENCODERS = {
 }
 
 
-def config_for_vda(encoder: str, max_h=518, max_w=518) -> ModelConfig:
+def config_for_vda(encoder: str, max_h=0, max_w=0) -> ModelConfig:
     e = VDA_ENCODERS[encoder]
     c = ModelConfig()
     c.hidden, c.layers, c.heads, c.mlp_hidden = e["hidden"], e["layers"], e["heads"], 4 * e["hidden"]

@@ -114,8 +114,8 @@ typedef struct d2s_model_config {
     float layer_norm_eps;
     float max_depth;     /* 1.0 for relative models */
     int32_t metric;      /* 0: final ReLU, 1: final sigmoid*max_depth */
-    int32_t max_batch;   /* workspace is sized for this many frames per call */
-    int32_t max_h, max_w;/* largest model input (multiples of patch) */
+    int32_t max_batch;   /* > 0: d2s_infer rejects B > max_batch (bounds the per-plan workspace); 0: no limit */
+    int32_t max_h, max_w;/* > 0: largest model input accepted; 0: no limit */
     /* Video-Depth-Anything (reference models/video_depth_anything/, depth.py:870-902): */
     int32_t temporal;    /* 0: Depth Anything V2 (per-frame).  1: streaming VDA: 4 temporal modules in the DPT head, one frame per
                             d2s_infer call (B must be 1), per-stream state = rings of the last 32 frames' K/V (vda2_s.py:177-224) */
@@ -135,9 +135,14 @@ int d2s_infer(d2s_handle h, const void *pixel_values, int in_dtype, void *depth_
  * streams — fewer, wider tiles.  Results agree to fp16 rounding (different accumulation splits), each policy is deterministic. */
 enum d2s_policy { D2S_POLICY_LATENCY = 0, D2S_POLICY_THROUGHPUT = 1 };
 int d2s_set_policy(d2s_handle h, int policy);
-/* temporal engines: forget the stream state (frame counter + K/V rings) of the plan(s) bound to `stream` — the next frame is a
- * first frame again (vda2_s.py:196 `if not self.transform`). */
+/* temporal engines: forget the video state bound to `stream` (frame counter + K/V rings; ONE state per stream and input size,
+ * shared by the plans of both policies and all dtypes) — the next frame is a first frame again (vda2_s.py:196
+ * `if not self.transform`).  All frames of one video must be submitted on one stream, in order. */
 int d2s_reset_stream(d2s_handle h, d2s_stream_t stream);
+/* Free everything the engine keeps for `stream`: its plans (activation buffers, graphs) and, for temporal engines, the video's
+ * state.  Call it before destroying a stream the engine has seen (a recycled stream handle would otherwise inherit the old
+ * video's window).  Host-synchronous.  The plan cache is also LRU-bounded (64 plans, env D2S_MAX_PLANS). */
+int d2s_release_stream(d2s_handle h, d2s_stream_t stream);
 /* Debug/parity taps: copy an internal activation (by name) to a caller buffer as fp32. */
 int d2s_debug_tap(d2s_handle h, const char *name, float *dst, size_t max_elems, size_t *n_elems, d2s_stream_t stream);
 size_t d2s_workspace_bytes(d2s_handle h);
@@ -159,7 +164,8 @@ typedef struct d2s_post_params {
     float foreground_scale; /* settings/10 */
     float aa_strength;    /* settings*2 */
     void *ema_state;      /* optional [H,W] compute_dtype persistent buffer (DepthStabilizer.prev) */
-    int32_t ema_valid;    /* 0: first frame (state := depth), 1: lerp */
+    int32_t ema_valid;    /* 0: first frame (state := depth), 1: lerp, 2: per element — a NaN in the state means "unset" (state :=
+                             depth there), so a state buffer filled with 0xFF bytes starts a stream without a host-side flag */
     float ema_alpha;      /* 0.9 */
     void *out_lowres;     /* optional [H,W] compute_dtype: the post-processed (+EMA) map before the upsample */
     void *workspace; size_t workspace_bytes;
@@ -169,6 +175,48 @@ int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream);
 
 /* overlay_fps: blends the "FPS: xx.x" glyph mask into an RGB image in place. */
 int d2s_overlay_fps(const d2s_image *rgb, int h, int w, const char *text, d2s_stream_t stream);
+
+/* ---- whole-frame pipeline: the caller side of the hot path ----
+ * Replaces the per-frame sequence main.py drives (reference main.py:232-262 process -> predict_depth, :1336-1341 make_sbs ->
+ * streamer.set_frame) with ONE call per frame.  A pipe owns `slots` frame slots; each slot has a CUDA stream, fixed device
+ * buffers, pinned host buffers (host_io) and CUDA graphs of the frame's ~150 kernels, so frames in flight overlap copy, network
+ * and warp.  Results are bit-identical to d2s_process -> d2s_preprocess -> d2s_infer -> d2s_postprocess -> d2s_make_sbs on the
+ * same frame (same kernels).  The DepthStabilizer EMA (depth.py:1865-1887) orders consecutive frames with an event between the
+ * two graphs of a frame; submit frames of one video in order.  One caller thread per pipe. */
+typedef struct d2s_pipe *d2s_pipe_handle;
+typedef struct d2s_pipe_config {
+    int32_t frame_h, frame_w, channels; /* captured frame: u8 HWC, BGRA (4) or BGR (3) (depth.py:549) */
+    int32_t target_height;        /* process(img, target_height): bilinear-antialias downscale when < frame_h (depth.py:555-566) */
+    int32_t rgb_dtype;            /* dtype of process()'s tensor: D2S_F16 (FP16 setting on) or D2S_F32 */
+    int32_t depth_resolution;     /* DEPTH_RESOLUTION (518) */
+    int32_t patch;                /* 14 */
+    float mean[3], std[3];        /* depth.py:1794-1799 */
+    int32_t metric;               /* post_process_depth / DepthStabilizer: the fields of d2s_post_params */
+    float percentile;
+    int32_t subsample_cap;
+    float gamma, foreground_scale, aa_strength;
+    int32_t use_temporal_smooth;
+    float ema_alpha;
+    double ipd_uv, depth_ratio, convergence;   /* make_sbs (depth.py:2186) */
+    int32_t display_mode, fill_16_9;
+    int32_t out_dtype;            /* packed frame [oh, ow, 3] HWC: D2S_F32 = what make_sbs returns (depth.py:2231), D2S_U8, D2S_F16 */
+    int32_t slots;                /* frames in flight (1..64); > 1 builds throughput-policy plans */
+    int32_t host_io;              /* 1: frames come from and results go to pinned HOST memory (H2D / D2H copies on the slot's stream) */
+    int32_t reserved[3];
+} d2s_pipe_config;
+int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2s_pipe_handle *out);
+int d2s_pipe_destroy(d2s_pipe_handle p);
+int d2s_pipe_geometry(d2s_pipe_handle p, int *h, int *w, int *model_h, int *model_w, int *out_h, int *out_w, size_t *frame_bytes, size_t *out_bytes);
+/* The slot's own buffers (valid for the life of the pipe): pinned host frame / result (host_io), device frame / result / depth
+ * [h,w] fp16 (what predict_depth returns), and its stream. */
+int d2s_pipe_slot_buffers(d2s_pipe_handle p, int slot, void **host_in, void **host_out, void **dev_in, void **dev_out, void **dev_depth, d2s_stream_t *stream);
+/* Enqueue one frame on `slot` and return.  frame: NULL = the slot's own input buffer, else a pinned host pointer (host_io) or a
+ * device pointer whose contents are complete on stream `frame_ready_on`.  The result lands in the slot's host_out / dev_out. */
+int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d2s_stream_t frame_ready_on);
+int d2s_pipe_wait(d2s_pipe_handle p, int slot);   /* block until the slot's frame is complete; the slot may then be reused */
+int d2s_pipe_reset(d2s_pipe_handle p);            /* new video: EMA state (and a temporal engine's window) forgotten; host-synchronous */
+int d2s_pipe_set_trace(d2s_pipe_handle p, int on);               /* record per-stage CUDA events on the frames submitted from now on */
+int d2s_pipe_slot_times(d2s_pipe_handle p, int slot, float ms[3]); /* after wait: process | resize+network+post | upsample+warp */
 
 /* ---- kernel-level parity hooks (used by tests/ only; fp16 operands, row-major) ----
  * d2s_debug_gemm:      C[M,N] = act(A[M,K] * Bw[N,K]^T + bias)   and/or   x32[M,N] += A*Bw^T + bias   (tcgen05 GEMM)

