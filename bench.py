@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — end-to-end frames/s of the depth-inference + SBS-warp hot path (BASELINE.json metric).
+"""bench.py — end-to-end frames/s of the depth-inference + SBS-warp hot path (BASELINE.json metric: "at 1080p & 4K").
 
-Workload at every N: BASELINE.json configs[1] per GPU — Depth Anything V2-Base, 1080p BGRA frames, batch 1,
-Full-SBS (model input 294x518, 778 tokens) — synthetic frames, seeded random-init weights (no network).  Frames shard
-across ranks with no per-frame collective ("scaling": "weak"); the only collective is one NCCL broadcast of the packed
-weight blob at init.
+Headline workload at every N (`value`, `e2e`): BASELINE.json configs[1] per GPU — Depth Anything V2-Base, 1080p BGRA frames,
+batch 1, Full-SBS (model input 294x518, 778 tokens).  The 4K half of the metric rides on the same line as the `large4k` block:
+configs[2] per GPU — DA-V2-Large, 8 concurrent 4K streams batched through the network (M = 6224 token rows), Full-SBS — with its own
+`value`, `e2e`, `roofline`, `cpu_baseline`; under torchrun the `config5` block is BASELINE configs[4]: 8 streams x 8 frames of 4K,
+stream s -> rank s mod G (strong scaling).  Synthetic frames, seeded random-init weights (no network).  Frames/streams shard across
+ranks with no per-frame collective ("scaling": "weak"); the only collective is one NCCL broadcast of the packed weights at init.
 
-    python bench.py --gpus 1 --steps 200 --warmup 10          # this repo's CUDA path
-    python bench.py --impl reference --steps 3 --warmup 1      # the reference's CPU path (oracle port), host cores
-One JSON line on stdout (rank 0).  `value` = frames/s with frames resident in HBM; `e2e` = the same through the
-reference-facing calls process -> predict_depth -> make_sbs with HOST buffers (H2D of the frame and D2H of the float32
-SBS frame inside the timed region).
+    python bench.py --gpus 1 --steps 200 --warmup 10            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1        # the reference's CPU path (oracle port), host cores
+    python bench.py --impl reference-cuda --steps 50             # the reference's torch-CUDA path (HF fp16 autocast + ATen) on this GPU
+One JSON line on stdout (rank 0).  `value` = frames/s with frames resident in HBM; `e2e` = the same through the repo's public API
+(StereoPipeline over d2s_pipe_*) with HOST buffers: H2D of the pinned BGRA frame and D2H of the float32 SBS frame inside the timed
+region.  A timed region is EXACTLY --steps frames between barrier + synchronize on both sides (max over ranks); it is repeated
+until >= 1 s of device time has been measured and the MEDIAN region is reported (`repeats`, `region_ms_min/max` give the spread).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -31,6 +36,7 @@ VARIANT = "Base"
 DISPLAY_MODE = "Full-SBS"
 DEPTH_RATIO = 2.0
 SEED = 0
+METRIC = "end-to-end frames/sec (depth infer + SBS warp)"
 
 
 def model_flops(cfg, Hm, Wm):
@@ -97,27 +103,57 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
 def build_hf_model(variant=VARIANT, seed=SEED):
     from desktop2stereo_b200.synth import make_hf_model   # seeded random-init weights (no checkpoints offline)
     return make_hf_model(variant, seed)
 
 
-def cpu_reference_fps(n_frames, warmup, threads):
-    """The reference's CPU path (oracle port: HF model under bf16 autocast + torch pre/post/warp) on the host cores."""
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arms (oracle/: the checker and the baselines — never the product path)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_fps(n_frames, warmup, threads, variant=VARIANT, h=H, w=W, mode=DISPLAY_MODE):
+    """The reference's CPU path (oracle port: HF model under bf16 autocast + torch pre/post/warp) on `threads` host cores."""
     import numpy as np
     import torch
     from oracle.cpu_pipeline import ReferenceCPUPipeline
+    old = torch.get_num_threads()
     torch.set_num_threads(threads)
-    pipe = ReferenceCPUPipeline(build_hf_model(), 518)
+    try:
+        pipe = ReferenceCPUPipeline(build_hf_model(variant), 518)
+        rng = np.random.default_rng(SEED)
+        frames = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for _ in range(2)]
+        for i in range(warmup):
+            pipe.frame(frames[i % 2], mode, DEPTH_RATIO)
+        t0 = time.perf_counter()
+        for i in range(n_frames):
+            out = pipe.frame(frames[i % 2], mode, DEPTH_RATIO)
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(old)
+    return n_frames / dt, dt
+
+
+def cuda_reference_fps(n_frames, warmup, dev, variant=VARIANT, h=H, w=W, mode=DISPLAY_MODE):
+    """The reference's torch-CUDA path restated with its own library calls (oracle/cuda_pipeline.py): HF module under fp16
+    autocast (cuBLAS / cuDNN / SDPA), ATen resize / topk / conv2d / grid_sample, one frame at a time with the H2D of the frame and
+    the .cpu() of the float32 result per frame — what main.py's loop does on an NVIDIA GPU."""
+    import numpy as np
+    import torch
+    from oracle.cuda_pipeline import ReferenceCUDAPipeline
+    pipe = ReferenceCUDAPipeline(build_hf_model(variant), dev, 518)
     rng = np.random.default_rng(SEED)
-    frames = [rng.integers(0, 256, (H, W, 4), dtype=np.uint8) for _ in range(2)]
+    frames = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for _ in range(4)]
     for i in range(warmup):
-        pipe.frame(frames[i % 2], DISPLAY_MODE, DEPTH_RATIO)
+        pipe.frame(frames[i % 4], mode, DEPTH_RATIO)
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for i in range(n_frames):
-        out = pipe.frame(frames[i % 2], DISPLAY_MODE, DEPTH_RATIO)
+        out = pipe.frame(frames[i % 4], mode, DEPTH_RATIO)       # ends in .cpu(): host-synchronous, like make_sbs
     dt = time.perf_counter() - t0
-    assert out.shape == (H, 2 * W, 3)
+    assert out.shape[2] == 3
+    del pipe
+    torch.cuda.empty_cache()
     return n_frames / dt, dt
 
 
@@ -126,26 +162,153 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    fps, dt = cpu_reference_fps(args.steps, max(args.warmup, 1), threads)
-    line = {
-        "impl": "reference", "metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": fps, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 autocast (CPU)", "data": "synthetic",
-        "config": {"workload": f"DA-V2-{VARIANT}, 1080p BGRA batch=1 -> {DISPLAY_MODE} (model input 294x518)"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} frames of the same 1080p workload, 1 frame per step"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    warm = max(args.warmup, 1)
+    if args.impl == "reference-cuda":
+        import torch
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        fps, dt = cuda_reference_fps(args.steps, max(args.warmup, 3), dev)
+        extra = {"impl": "reference-cuda", "dtype": "fp16 autocast (torch CUDA: cuBLAS/cuDNN/SDPA + ATen)",
+                 "reference_cuda": {"value": fps, "unit": "frames/s", "kind": "port", "sample": f"{args.steps} frames, one at a time, H2D + .cpu() per frame"},
+                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": H * W * 4, "d2h_bytes_per_step": H * 2 * W * 3 * 4}}
+    else:
+        fps, dt = cpu_reference_fps(args.steps, warm, threads)
+        extra = {"impl": "reference", "dtype": "bf16 autocast (CPU)",
+                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                  "sample": f"{args.steps} frames of the same 1080p workload, 1 frame per step"},
+                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": WORKLOADS["base1080"][4] + ", per GPU"}}
+    line.update(extra)
     print(json.dumps(line))
     return 0
 
 
 WORKLOADS = {
-    # name: (variant, frame h, frame w, frames per engine call, description)
+    # name: (variant, frame h, frame w, streams per submit, description)
     "base1080": ("Base", 1080, 1920, 1, "BASELINE.json configs[1]: DA-V2-Base, 1080p BGRA batch=1 -> Full-SBS (model input 294x518, 778 tokens)"),
     "large4k": ("Large", 2160, 3840, 8, "BASELINE.json configs[2]: DA-V2-Large, 4K BGRA batch=8 -> Full-SBS (model input 8 x 294x518, 6224 token rows)"),
     "vda1080": ("vits", 1080, 1920, 1, "BASELINE.json configs[3]: streaming Video-Depth-Anything, 1080p, 32-frame temporal window, one video per CUDA stream"),
 }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the product arm
+# ---------------------------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        # one process per GPU, pinned to the cores (and, by first touch, the memory) of the GPU's NUMA node — before any pinned
+        # buffer exists
+        from desktop2stereo_b200.sharding import bind_to_gpu_numa
+        self.numa = bind_to_gpu_numa(self.local, self.local, int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world))))
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.warmup = max(args.warmup, 3)
+        self.peaks, self.peak_src = load_peaks()
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def region(self, fn, steps):
+        """EXACTLY `steps` steps through fn, device-timed between barrier + synchronize on both sides, max over ranks -> ms"""
+        torch = self.torch
+        self.barrier(); torch.cuda.synchronize()
+        s, e = self.ev(), self.ev()
+        s.record()
+        fn(range(steps))
+        torch.cuda.synchronize()
+        e.record()
+        torch.cuda.synchronize(); self.barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item()
+
+    def timed(self, fn, steps, min_s=1.0, max_repeats=400):
+        """the K-step region repeated until >= min_s of device time: median region + spread (every rank runs the same count)"""
+        first = self.region(fn, steps)
+        reps = int(min(max(math.ceil(min_s * 1e3 / max(first, 1e-3)), 3), max_repeats))
+        ms = sorted([first] + [self.region(fn, steps) for _ in range(reps - 1)])
+        return {"ms": ms[len(ms) // 2], "min": ms[0], "max": ms[-1], "repeats": len(ms)}
+
+
+def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, out_dtypes, want_device=True):
+    """device-resident and host-buffer legs of one workload through StereoPipeline; a step = one submit = `streams` frames"""
+    import numpy as np
+    torch = B.torch
+    from desktop2stereo_b200 import _lib
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    L = _lib.lib()
+    res = {}
+    ring_d, ring_h = len(frames_dev), len(frames_host)
+    warm = max(B.warmup, 2 * slots)
+    fpp = streams                                  # frames per step
+    oshape = ((streams,) if streams > 1 else ()) + (h, 2 * w, 3)
+    if want_device:
+        pipe = StereoPipeline(depth_slots=slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, streams=streams)
+
+        def run_dev(idx):
+            for _ in pipe.run((frames_dev[i % ring_d] for i in idx), host=False):
+                pass
+        run_dev(range(warm))
+        torch.cuda.synchronize()
+        clocks = ClockSampler(B.local); clocks.start()
+        l0 = L.d2s_launch_count()
+        pipe.trace = []
+        torch.cuda.profiler.start()          # no-op unless run under `ncu --profile-from-start off`
+        t = B.timed(run_dev, steps)
+        torch.cuda.profiler.stop()
+        launches_per_region = (L.d2s_launch_count() - l0) / t["repeats"]
+        res["clocks"] = clocks.stop()
+        st = np.array(pipe.trace) if pipe.trace else np.zeros((1, 3))
+        pipe.trace = None
+        res["device"] = dict(t, fps=B.world * steps * fpp / (t["ms"] / 1e3), launches=int(round(launches_per_region)),
+                             stage_ms=dict(zip(["process", "resize+network+postprocess", "upsample+warp"], np.median(st, 0).tolist())))
+        pipe.close()
+    for name, odt in out_dtypes:
+        pipe = StereoPipeline(depth_slots=slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, out_dtype=odt, streams=streams)
+
+        def run_host(idx, p=pipe):
+            r = None
+            for r in p.run((frames_host[i % ring_h] for i in idx), host=True):   # pinned host frames -> H2D inside the timed region
+                pass
+            return r
+        r = run_host(range(warm))
+        assert tuple(r.shape) == oshape and r.dtype == {torch.float32: np.float32, torch.uint8: np.uint8}[odt]
+        t = B.timed(run_host, steps)
+        es = 4 if odt == torch.float32 else 1
+        h2d, d2h = fpp * h * w * 4, fpp * h * 2 * w * 3 * es
+        fps = B.world * steps * fpp / (t["ms"] / 1e3)
+        res[name] = dict(t, fps=fps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, pcie_gbs_per_gpu=(h2d + d2h) * fps / fpp / B.world / 1e9)
+        pipe.close()
+    return res
+
+
+def host_copy_bandwidth(B, nbytes=256 << 20):
+    """measured D2H and H2D rates of this rank's pinned memory (all ranks copy at the same time): names the limiter of the fp32 e2e row"""
+    torch = B.torch
+    hbuf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dbuf = torch.empty(nbytes, dtype=torch.uint8, device=B.dev)
+    out = {}
+    for name, (dst, src) in {"d2h_gbs": (hbuf, dbuf), "h2d_gbs": (dbuf, hbuf)}.items():
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        ms = B.region(lambda idx: [dst.copy_(src, non_blocking=True) for _ in idx], 8)
+        out[name] = 8 * nbytes / (ms / 1e3) / 1e9
+    return out
 
 
 def main():
@@ -153,83 +316,44 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large4k", action="store_true", help="skip the 4K (configs[2] / configs[4]) block")
+    ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--slots", type=int, default=8, help="frames in flight (CUDA streams) in the pipelined legs")
     ap.add_argument("--vda-encoder", default="vits", choices=["vits", "vitb", "vitl"])
-    ap.add_argument("--workload", default="base1080", choices=sorted(WORKLOADS),
-                    help="base1080 is the headline (configs[1]); large4k (configs[2]) is an extra measurement, not the default line")
+    ap.add_argument("--workload", default="base1080", choices=["base1080", "vda1080"],
+                    help="base1080 is the headline (configs[1], with the large4k block); vda1080 (configs[3]) is an extra measurement")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl != "b200":
         return run_reference(args)
-    if args.workload == "large4k":
-        return run_large4k(args)
     if args.workload == "vda1080":
         return run_vda1080(args)
 
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    B = Bench(args)
+    torch, dev, world, rank = B.torch, B.dev, B.world, B.rank
     from desktop2stereo_b200 import _lib, depth
     from desktop2stereo_b200.stereo import make_sbs_core
     L = _lib.lib()
-    warmup = max(args.warmup, 3)
+    peaks, src = B.peaks, B.peak_src
+
+    # ================= headline: configs[1] =================
     engine, cfg = build_engine(VARIANT, rank, world, dev)
     depth.init(engine=engine, device=dev)
-
-    # ---- synthetic frames: a ring larger than L2 so no timed iteration re-reads a cached frame ----
-    RING = 24
+    RING = 24          # a ring larger than L2 so no timed iteration re-reads a cached frame
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     frames = [torch.randint(0, 256, (H, W, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(RING)]
-    host_frames = [f.cpu().pin_memory() for f in frames[:4]]   # pinned host copies for the end-to-end leg
+    host_frames = [f.cpu().pin_memory() for f in frames[:4]]   # pinned host copies for the end-to-end legs
     host_np = [t.numpy() for t in host_frames]
 
-    from desktop2stereo_b200.pipeline import StereoPipeline
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def timed(fn, steps):
-        """`steps` frames through fn (a callable that consumes an iterable of frame indices), device-timed, max over ranks."""
-        barrier(); torch.cuda.synchronize()
-        s, e = ev(), ev()
-        s.record()
-        fn(range(steps))
-        torch.cuda.synchronize()
-        e.record()
-        torch.cuda.synchronize(); barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    def stage_stats(trace):
-        """per-stage device time from the events recorded on each frame's stream: median (robust to a host hiccup) and mean"""
-        torch.cuda.synchronize()
-        st = np.array([list(e) if not hasattr(e[0], "elapsed_time") else [e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in trace])
-        names = ["process", "predict_depth", "warp"]
-        return dict(zip(names, np.median(st, 0).tolist())), dict(zip(names, st.mean(0).tolist()))
-
-    # ---- (1) serial, one stream: the drop-in calls back to back; isolates per-stage device times ----
+    # ---- serial, one stream: the drop-in calls back to back; isolates per-stage device times (latency view) ----
     serial_trace = []
 
     def serial_device(idx):
         for i in idx:
-            e = [ev() for _ in range(4)]
+            e = [B.ev() for _ in range(4)]
             e[0].record()
             rgb = depth.process(frames[i % RING], H)
             e[1].record()
@@ -247,113 +371,268 @@ def main():
             out = depth.make_sbs(rgb, d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE)   # D2H float32 HWC + sync
         return out
 
-    out = serial_device(range(warmup))
+    out = serial_device(range(B.warmup))
     assert tuple(out.shape) == (H, 2 * W, 3)
     serial_trace.clear()
     n_serial = min(args.steps, 100)
-    ms_serial = timed(serial_device, n_serial)
-    serial_stage_ms, serial_stage_mean = stage_stats(serial_trace)
-    serial_e2e(range(warmup))
-    ms_serial_e2e = timed(serial_e2e, n_serial)
-
-    # ---- (2) pipelined: `slots` frames in flight on `slots` CUDA streams (what main.py's 3-thread loop does) ----
-    pipe = StereoPipeline(depth_slots=args.slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO)
-
-    def pipe_device(idx):
-        for _ in pipe.run((frames[i % RING] for i in idx), host=False):
-            pass
-
-    def pipe_e2e(idx, p=pipe):
-        for res in p.run((host_frames[i % 4] for i in idx), host=True):   # pinned host frames -> H2D inside the timed region
-            pass
-        return res
-
-    pipe_device(range(max(warmup, 2 * args.slots)))
+    ms_serial = B.region(serial_device, n_serial)
     torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches0 = L.d2s_launch_count()
-    pipe.trace = []
-    torch.cuda.profiler.start()          # no-op unless run under `ncu --profile-from-start off`
-    ms = timed(pipe_device, args.steps)
-    torch.cuda.profiler.stop()
-    launches = L.d2s_launch_count() - launches0
-    clk = clocks.stop()
-    stage_ms, _ = stage_stats(pipe.trace)   # events recorded on each frame's stream INSIDE the timed region (streams overlap)
-    pipe.trace = None
-    fps = world * args.steps / (ms / 1e3)
+    st = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in serial_trace])
+    serial_stage_ms = dict(zip(["process", "predict_depth", "warp"], np.median(st, 0).tolist()))
+    serial_e2e(range(B.warmup))
+    ms_serial_e2e = B.region(serial_e2e, n_serial)
 
-    res = pipe_e2e(range(max(warmup, 2 * args.slots)))
-    assert res.shape == (H, 2 * W, 3) and res.dtype == np.float32
-    ms_e2e = timed(pipe_e2e, args.steps)
-    fps_e2e = world * args.steps / (ms_e2e / 1e3)
-    h2d, d2h = H * W * 4, H * 2 * W * 3 * 4
-
-    # the same end-to-end loop with the 4x smaller u8 frame packed on the device (not the reference's return type)
-    pipe8 = StereoPipeline(depth_slots=args.slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, out_dtype=torch.uint8)
-    res8 = pipe_e2e(range(max(warmup, 2 * args.slots)), pipe8)
-    assert res8.shape == (H, 2 * W, 3) and res8.dtype == np.uint8
-    ms_e2e8 = timed(lambda idx: pipe_e2e(idx, pipe8), args.steps)
+    legs = pipe_legs(B, depth, frames, host_frames, H, W, 1, args.slots, args.steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8)])
+    dv, e2e, e2e8 = legs["device"], legs["e2e"], legs["e2e_u8"]
+    host_bw = host_copy_bandwidth(B)
 
     # ---- rooflines (denominators: MEASURED_PEAKS.json, else the profiling guide's fallback) ----
-    peaks, src = load_peaks()
-    # warp kernel: fp16 CHW rgb in (6 B/px) + fp16 depth in (2 B/px) + fp32 HWC Full-SBS out (24 B/px); timed alone (serial leg:
-    # one frame at a time on one stream, CUDA events on that stream) so the duration is the kernel's, not a share of a busy GPU
+    traffic = load_traffic()
+    # warp kernel: fp16 CHW rgb in (6 B/px) + fp16 depth in (2 B/px) + fp32 HWC Full-SBS out (24 B/px); timed alone (serial leg: one
+    # frame at a time on one stream, CUDA events on that stream) so the duration is the kernel's, not a share of a busy GPU
     warp_bytes = H * W * (6 + 2 + 24)
     warp_gbs = warp_bytes / (serial_stage_ms["warp"] * 1e-3) / 1e9
-    # the network is replayed as ONE CUDA-graph launch per frame (~140 kernels, the tcgen05 GEMM is ~60 % of its time):
-    #   isolated: duration of one launch alone on the GPU (serial leg) -> batch-1 latency view
-    #   in the timed region: `slots` launches overlap, so GPU time per launch = timed region / launches
     Hm, Wm = 294, 518
     gflop = model_flops(cfg, Hm, Wm) / 1e9
     net_tflops_iso = gflop / (serial_stage_ms["predict_depth"] * 1e-3) / 1e3
-    net_tflops = gflop * args.steps / (ms * 1e-3) / 1e3
-    roofline_warp = {"kernel": "warp_sbs_fast_kernel", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": 16.63e6 + 1.22e6, "traffic_note": "dram__bytes_read + dram__bytes_write of one isolated launch under ncu --set full (profiles/r1_warp_v4_ncu_full.txt): the 49.8 MB written stay in the 126 MB L2 during an isolated replay",
-                     "peak_source": src, "bytes_per_launch": warp_bytes,
+    net_tflops = gflop * args.steps / (dv["ms"] * 1e-3) / 1e3
+    roofline_warp = {"kernel": "warp_sbs kernel (1080p)", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": traffic.get("warp_1080p"), "peak_source": src, "bytes_per_launch": warp_bytes,
                      "duration_ms": serial_stage_ms["warp"], "timed": "alone on the GPU (serial leg), CUDA events on its stream, median of %d" % n_serial,
                      "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS"}
-    roofline_net = {"kernel": "depth network, one graph launch per frame (preprocess + ViT-B + DPT on gemm_tc_kernel/tcgen05 + postprocess)",
+    roofline_net = {"kernel": "whole frame graph (resize + ViT-B + DPT on gemm_tc_kernel/tcgen05 + postprocess + warp), all kernels",
                     "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": src, "gflop_per_launch": gflop,
-                    "duration_ms": ms / args.steps, "timed": "timed region / launches with %d launches in flight" % args.slots,
+                    "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": src, "gflop_per_frame": gflop,
+                    "duration_ms": dv["ms"] / args.steps, "timed": "timed region / frames with %d frames in flight" % args.slots,
                     "isolated": {"achieved": net_tflops_iso, "frac": net_tflops_iso / peaks["bf16_tflops_sustained"],
-                                 "duration_ms": serial_stage_ms["predict_depth"], "note": "one launch alone on the GPU: batch-1 is latency-bound"}}
+                                 "duration_ms": serial_stage_ms["predict_depth"], "note": "one frame alone on the GPU: batch-1 is latency-bound"}}
+    gemms = gemm_rooflines(dev, peaks, src)
+    # the dominant kernel = the tcgen05 GEMM (one kernel template; ~60 % of a frame's GPU time): its four encoder-layer launches at
+    # THIS workload's shapes, timed live in a graph of back-to-back launches on their own stream; achieved = algorithmic FLOPs per
+    # launch / average launch duration
+    own = [r for r in gemms if r["M"] == 778]
+    fl = sum(2.0 * r["M"] * r["N"] * r["K"] for r in own)
+    us = sum(r["duration_us"] for r in own)
+    roofline = {"kernel": "gemm_tc_kernel (tcgen05), the 4 GEMMs of one ViT-B encoder layer at M = 778 (qkv, proj, fc1+GELU, fc2)", "bound": "tensor",
+                "achieved": fl / us / 1e6, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / peaks["bf16_tflops"],
+                "traffic": traffic.get("gemm_m778"), "peak_source": src + " (burst: kernel timed alone)", "flops_per_launch": fl / len(own),
+                "duration_us_per_launch": us / len(own), "launches": len(own),
+                "timed": "live: graph of 20 back-to-back launches per shape, CUDA events on their stream, L2-warm",
+                "note": "batch-1 shapes fill 42-126 of 148 SMs for ~10 us: latency-bound; the same kernel at batch 8 is in large4k.roofline"}
 
     line = {
-        "metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": fps, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
-        "config": {"workload": f"DA-V2-{VARIANT}, 1080p BGRA batch=1 -> {DISPLAY_MODE} (model input 294x518, 778 tokens), per GPU",
-                   "l2": f"ring of {RING} distinct frames ({RING * H * W * 4 / 1e6:.0f} MB) > 126 MB L2", "parallelism": f"frames sharded x{world}; {args.slots} frames in flight per GPU",
-                   "weights": "seeded random init, one NCCL broadcast at init" if world > 1 else "seeded random init"},
-        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "pcie_gbs": (h2d + d2h) * fps_e2e / world / 1e9,
-                "api": f"StereoPipeline({args.slots} frames in flight): pinned BGRA frame -> process -> predict_depth -> make_sbs -> float32 HWC host frame",
-                "note": "bounded by the device->host copy of the reference-faithful float32 frame (49.8 MB/frame)"},
-        "e2e_u8": {"value": world * args.steps / (ms_e2e8 / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * 2 * W * 3,
-                   "note": "same loop, uint8 HWC frame packed by the warp kernel (4x fewer bytes over PCIe); not the reference's return dtype"},
-        "gpu_launches": int(launches), "clocks": clk, "stage_ms": stage_ms,
-        "serial": {"note": "same calls, one frame at a time on one stream (latency view); stage_ms = medians", "steps": n_serial,
-                   "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
-                   "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms,
-                   "stage_ms_mean": serial_stage_mean},
-        "roofline": roofline_net, "roofline_warp": roofline_warp, "roofline_net": roofline_net,
-        "roofline_gemm": gemm_rooflines(dev, peaks, src),
+        "metric": METRIC, "value": dv["fps"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": B.warmup,
+        "ms_per_step": dv["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
+        "repeats": dv["repeats"], "region_ms_min": dv["min"], "region_ms_max": dv["max"],
+        "config": {"workload": WORKLOADS["base1080"][4] + ", per GPU",
+                   "l2": f"ring of {RING} distinct frames ({RING * H * W * 4 / 1e6:.0f} MB) > 126 MB L2",
+                   "parallelism": f"frames sharded x{world}; {args.slots} frames in flight per GPU; one process per GPU bound to its NUMA node",
+                   "weights": "seeded random init, one NCCL broadcast at init" if world > 1 else "seeded random init",
+                   "timing": "median of `repeats` regions of exactly `steps` frames (>= 1 s of device time in total)"},
+        "e2e": {"value": e2e["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
+                "ms_per_step": e2e["ms"] / args.steps, "repeats": e2e["repeats"], "pcie_gbs_per_gpu": e2e["pcie_gbs_per_gpu"],
+                "api": f"StereoPipeline({args.slots} frames in flight) over d2s_pipe_*: pinned BGRA frame -> process -> predict_depth -> make_sbs -> float32 HWC host frame",
+                "limiter": "the device->host copy of the reference-faithful float32 frame (49.8 MB/frame); measured pinned-copy rates in host_copy"},
+        "gpu_launches": dv["launches"], "clocks": legs["clocks"], "numa": B.numa, "host_copy": host_bw,
+        "legs": {
+            "e2e_u8": {"value": e2e8["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2e8["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e8["d2h_bytes_per_step"],
+                       "pcie_gbs_per_gpu": e2e8["pcie_gbs_per_gpu"],
+                       "note": "same loop, uint8 HWC frame packed by the warp kernel (4x fewer bytes over PCIe); what streamer.set_frame encodes (streamer.py:250-256)"},
+            "serial": {"note": "the drop-in calls one frame at a time on one stream (latency view); stage_ms = medians", "steps": n_serial,
+                       "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
+                       "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms},
+            "stage_ms_in_flight": dv["stage_ms"],
+        },
+        "roofline": roofline, "roofline_warp": roofline_warp, "roofline_net": roofline_net, "roofline_gemm": gemms,
     }
+    del frames, host_frames, host_np
+    depth.model_wraper = None
+    engine.close()
+    torch.cuda.empty_cache()
+
+    # ================= the 4K half of the metric: configs[2] per GPU, configs[4] across GPUs =================
+    if not args.no_large4k:
+        line["large4k"] = large4k_block(B, args)
+    # ================= reference arms measured in the same run (rank 0, N = 1) =================
+    if rank == 0 and world == 1 and not args.no_reference_cuda:
+        rfps, rdt = cuda_reference_fps(30, 5, dev)
+        line["reference_cuda"] = {"value": rfps, "unit": "frames/s", "kind": "port", "workload": "base1080",
+                                  "sample": f"30 frames after 5 warm-ups ({rdt:.2f} s), one frame at a time with H2D + .cpu() per frame",
+                                  "what": "the reference's torch-CUDA path: HF module under fp16 autocast (cuBLAS/cuDNN/SDPA) + ATen resize/topk/conv2d/grid_sample (oracle/cuda_pipeline.py)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cfps, cdt = cpu_reference_fps(args.cpu_frames, 1, threads)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_frames} frames of the same 1080p workload after 1 warm-up ({cdt:.1f} s)"}
+        c1, c1dt = cpu_reference_fps(2, 1, 1)
+        line["cpu_baseline_1thread"] = {"value": c1, "unit": "frames/s", "cores": 1, "kind": "port",
+                                        "sample": f"2 frames after 1 warm-up ({c1dt:.1f} s); torch.set_num_threads(1) is what the reference ships (depth.py:19)"}
+        line["config1"] = config1_block(B, threads)
+    # compact copies inside the keys the driver's parser keeps (e2e / roofline / cpu_baseline), and a summary as the LAST key so the
+    # tail of the line carries the 1080p and the 4K numbers side by side
+    l4 = line.get("large4k")
+    line["e2e"]["legs"] = {"e2e_u8": e2e8["fps"], "serial_ms_per_frame_device": ms_serial / n_serial, "serial_ms_per_frame_e2e": ms_serial_e2e / n_serial}
+    line["roofline"]["others"] = {"warp_1080p_hbm_frac": roofline_warp["frac"], "frame_graph_tensor_frac_in_flight": roofline_net["frac"],
+                                  "frame_graph_tensor_frac_alone": roofline_net["isolated"]["frac"]}
+    if l4:
+        line["e2e"]["legs"].update({"large4k_value": l4["value"], "large4k_e2e_fp32": l4["e2e"]["value"], "large4k_e2e_u8": l4["e2e_u8"]["value"]})
+        line["roofline"]["others"].update({"warp_4k_hbm_frac": l4["roofline_warp"]["frac"], "gemm_m6224_tensor_frac": l4["roofline"]["frac"],
+                                           "large4k_step_graph_tensor_frac": l4["roofline_net"]["frac"]})
+        if "config5" in l4 and "value" in l4["config5"]:
+            line["e2e"]["legs"].update({"config5_value": l4["config5"]["value"], "config5_e2e_fp32": l4["config5"]["e2e"], "config5_e2e_u8": l4["config5"]["e2e_u8"]})
+    if "cpu_baseline" in line:
+        line["cpu_baseline"]["one_thread"] = line["cpu_baseline_1thread"]["value"]
+        if l4 and "cpu_baseline" in l4:
+            line["cpu_baseline"]["large4k_all_cores"] = l4["cpu_baseline"]["value"]
+        line["cpu_baseline"]["config1_one_thread"] = line["config1"]["cpu_1thread"]["value"]
+        if "reference_cuda" in line:
+            line["cpu_baseline"]["reference_torch_cuda_same_gpu"] = line["reference_cuda"]["value"]
+    line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"]},
+                       "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"]} if l4 else None),
+                       "reference_cuda_base1080": line.get("reference_cuda", {}).get("value"), "unit": "frames/s", "n_gpus": world}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
     return 0
 
 
-def gemm_rooflines(dev, peaks, src):
+def large4k_block(B, args):
+    """configs[2] per GPU: DA-V2-Large, 8 concurrent 4K streams, one frame of each per step, batched through the network (6224 token
+    rows) -> 8 Full-SBS frames.  Under torchrun also configs[4]: 8 streams x 8 frames in total, stream s -> rank s mod G."""
+    torch, dev, world, rank = B.torch, B.dev, B.world, B.rank
+    from desktop2stereo_b200 import depth
+    variant, h, w, S, desc = WORKLOADS["large4k"]
+    engine, cfg = build_engine(variant, rank, world, dev)
+    depth.init(engine=engine, device=dev)
+    g = torch.Generator(device=dev).manual_seed(SEED + 100 + rank)
+    RING = 2                                   # 2 x 8 x 33 MB = 531 MB of distinct frames > L2
+    frames = [torch.randint(0, 256, (S, h, w, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(RING)]
+    host_frames = [f.cpu().pin_memory() for f in frames]
+    steps = max(4, min(args.steps // 8, 16))    # a step = one frame of each of the 8 streams
+    slots = 2
+    legs = pipe_legs(B, depth, frames, host_frames, h, w, S, slots, steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8)])
+    dv, e2e, e2e8 = legs["device"], legs["e2e"], legs["e2e_u8"]
+    gflop = S * model_flops(cfg, 294, 518) / 1e9
+    step_ms = dv["ms"] / steps
+    net_tf = gflop / (step_ms * 1e-3) / 1e3
+    gem = [r for r in gemm_rooflines(dev, B.peaks, B.peak_src, shapes="large") ]
+    fl = sum(2.0 * r["M"] * r["N"] * r["K"] for r in gem); us = sum(r["duration_us"] for r in gem)
+    traffic = load_traffic()
+    out = {"workload": desc + ", per GPU", "value": dv["fps"], "unit": "frames/s", "steps": steps, "frames_per_step": S, "ms_per_step": step_ms,
+           "repeats": dv["repeats"], "slots": slots, "gpu_launches": dv["launches"], "stage_ms_in_flight": dv["stage_ms"], "clocks": legs["clocks"],
+           "l2": "2 batches of 8 distinct 4K frames (531 MB) > 126 MB L2",
+           "e2e": {"value": e2e["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
+                   "pcie_gbs_per_gpu": e2e["pcie_gbs_per_gpu"], "api": "StereoPipeline(streams=8, 2 steps in flight): pinned 4K BGRA frames -> float32 HWC host frames",
+                   "limiter": "PCIe: 33 MB in + 199 MB out per 4K frame"},
+           "e2e_u8": {"value": e2e8["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2e8["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e8["d2h_bytes_per_step"],
+                      "pcie_gbs_per_gpu": e2e8["pcie_gbs_per_gpu"]},
+           "target": {"north_star": ">= 60 frames/s end-to-end 4K depth + Full-SBS on 1 x B200", "met_fp32": e2e["fps"] / world >= 60, "met_u8": e2e8["fps"] / world >= 60},
+           "roofline": {"kernel": "gemm_tc_persistent_kernel (tcgen05, cta_group::2), the 4 GEMMs of one ViT-L encoder layer at M = 6224", "bound": "tensor",
+                        "achieved": fl / us / 1e6, "peak": B.peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / B.peaks["bf16_tflops"],
+                        "traffic": traffic.get("gemm_m6224"), "peak_source": B.peak_src + " (burst)", "per_shape": gem,
+                        "timed": "live: graph of 20 back-to-back launches per shape, CUDA events on their stream"},
+           "roofline_net": {"kernel": "whole step graph (8 x resize + ViT-L + DPT batch 8 + 8 x postprocess + 8 x warp)", "bound": "tensor",
+                            "achieved": net_tf, "peak": B.peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": net_tf / B.peaks["bf16_tflops_sustained"],
+                            "gflop_per_step": gflop, "duration_ms": step_ms},
+           "roofline_warp": warp_roofline_4k(B, traffic)}
+    if world > 1:      # configs[4]: 8 streams in total, stream s -> rank s % G, 8 frames per stream
+        from desktop2stereo_b200.sharding import streams_for_rank
+        mine = streams_for_rank(8, rank, world)
+        sl = len(mine)
+        f5 = [f[:sl].contiguous() for f in frames]
+        h5 = [f.cpu().pin_memory() for f in f5]
+        l5 = pipe_legs(B, depth, f5, h5, h, w, sl, 2, 8, [("e2e", torch.float32), ("e2e_u8", torch.uint8)])
+        # every rank runs 8 steps of its own streams; whole job = 64 frames per region
+        scale = 64.0 / (world * 8 * sl)
+        out["config5"] = {"workload": "BASELINE.json configs[4]: 8 concurrent 4K streams x 8 frames, DA-V2-Large -> Full-SBS; stream s -> rank s mod G",
+                          "scaling": "strong", "streams_per_gpu": sl, "frames_per_region": 64,
+                          "value": l5["device"]["fps"] * scale, "e2e": l5["e2e"]["fps"] * scale, "e2e_u8": l5["e2e_u8"]["fps"] * scale, "unit": "frames/s",
+                          "repeats": l5["device"]["repeats"]}
+    else:
+        out["config5"] = {"note": "at 1 GPU configs[4] (8 streams on one GPU) is this block's own workload"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cfps, cdt = cpu_reference_fps(2, 1, threads, variant, h, w)
+        out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": f"2 4K frames of DA-V2-Large after 1 warm-up ({cdt:.1f} s), one frame at a time"}
+    depth.model_wraper = None
+    engine.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def warp_roofline_4k(B, traffic):
+    """the warp kernel alone at 4K, IN FLIGHT over a ring of frames larger than L2 (so its writes leave the L2): CUDA events around a
+    graph of 16 launches on 16 distinct input/output sets"""
+    torch, dev = B.torch, B.dev
+    from desktop2stereo_b200.stereo import make_sbs_core
+    h, w, n = 2160, 3840, 6
+    g = torch.Generator(device=dev).manual_seed(7)
+    rgbs = [torch.randint(0, 256, (3, h, w), generator=g, device=dev, dtype=torch.uint8).half() for _ in range(n)]
+    deps = [torch.rand((h, w), generator=g, device=dev).half() for _ in range(n)]
+    outs = [torch.empty((h, 2 * w, 3), device=dev, dtype=torch.float32) for _ in range(n)]
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        for i in range(n):
+            make_sbs_core(rgbs[i], deps[i], depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC", out=outs[i])
+        st.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for i in range(n):
+                make_sbs_core(rgbs[i], deps[i], depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC", out=outs[i])
+        gr.replay(); st.synchronize()
+        s_, e_ = B.ev(), B.ev()
+        s_.record(st); gr.replay(); gr.replay(); e_.record(st); st.synchronize()
+    ms = s_.elapsed_time(e_) / (2 * n)
+    nbytes = h * w * (6 + 2 + 24)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "warp_sbs kernel (4K)", "bound": "hbm", "achieved": gbs, "peak": B.peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": gbs / B.peaks["hbm_gbs"], "traffic": traffic.get("warp_4k"), "bytes_per_launch": nbytes, "duration_ms": ms,
+            "timed": f"live: {2 * n} launches over {n} distinct 4K frame sets ({n * nbytes / 1e6:.0f} MB > L2) in a CUDA graph, events on its stream",
+            "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS", "peak_source": B.peak_src}
+
+
+def config1_block(B, threads):
+    """BASELINE configs[0]: DA-V2-Small, one 518x518 frame -> Half-SBS: the reference's CPU path (1 thread as shipped, and all
+    cores) next to this repo's serial drop-in calls on the GPU."""
+    torch, dev = B.torch, B.dev
+    import numpy as np
+    from desktop2stereo_b200 import depth
+    from desktop2stereo_b200.engine import B200Engine
+    c1, d1 = cpu_reference_fps(2, 1, 1, "Small", 518, 518, "Half-SBS")
+    ca, da = cpu_reference_fps(4, 1, threads, "Small", 518, 518, "Half-SBS")
+    eng = B200Engine.from_hf_model(build_hf_model("Small"), dev)
+    depth.init(engine=eng, device=dev)
+    rng = np.random.default_rng(0)
+    frame = torch.from_numpy(rng.integers(0, 256, (518, 518, 4), dtype=np.uint8)).pin_memory().numpy()
+
+    def run(idx):
+        for _ in idx:
+            rgb = depth.process(frame, 518)
+            out = depth.make_sbs(rgb, depth.predict_depth(rgb), display_mode="Half-SBS")
+        return out
+    assert run(range(5)).shape == (518, 518, 3)
+    ms = B.region(run, 50)
+    depth.model_wraper = None
+    eng.close()
+    return {"workload": "BASELINE.json configs[0]: DA-V2-Small, 518x518 frame -> Half-SBS (model input 518x518, 1370 tokens)",
+            "cpu_1thread": {"value": c1, "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"2 frames ({d1:.1f} s)"},
+            "cpu_all_cores": {"value": ca, "unit": "frames/s", "cores": threads, "kind": "port", "sample": f"4 frames ({da:.1f} s)"},
+            "b200_serial_e2e": {"value": 50 / (ms / 1e3), "unit": "frames/s", "note": "process -> predict_depth -> make_sbs, host frame in, float32 host frame out, one at a time"}}
+
+
+def load_traffic():
+    """per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernels from this round's ncu --set full
+    captures: profiles/traffic.json, written by tools/ncu_summary.py from the committed captures (never typed in here)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+def gemm_rooflines(dev, peaks, src, shapes="base"):
     """The tcgen05 GEMM kernel alone, timed live with CUDA events around a graph of back-to-back launches (so that host launch
     cost is not what is measured): the headline workload's own shapes (M = 778 token rows: latency-bound) and the same layers at
     batch 8 (M = 6224: persistent kernel).  Peak = the measured cuBLAS bf16 BURST figure (a kernel timed in isolation)."""
@@ -361,15 +640,18 @@ def gemm_rooflines(dev, peaks, src):
     from desktop2stereo_b200 import _lib
     L = _lib.lib()
     out = []
-    for (name, M, N, K, x32) in [("qkv, batch 1", 778, 2304, 768, False), ("fc2 (+residual stream), batch 1", 778, 768, 3072, True),
-                                 ("qkv, batch 8 (ViT-L)", 6224, 3072, 1024, False), ("fc1, batch 8 (ViT-L)", 6224, 4096, 1024, False)]:
+    table = {"base": [("qkv, batch 1 (ViT-B)", 778, 2304, 768, False, 0), ("proj (+residual stream)", 778, 768, 768, True, 0),
+                      ("fc1 + GELU", 778, 3072, 768, False, 1), ("fc2 (+residual stream)", 778, 768, 3072, True, 0)],
+             "large": [("qkv, batch 8 (ViT-L)", 6224, 3072, 1024, False, 0), ("proj (+residual stream)", 6224, 1024, 1024, True, 0),
+                       ("fc1 + GELU", 6224, 4096, 1024, False, 1), ("fc2 (+residual stream)", 6224, 1024, 4096, True, 0)]}
+    for (name, M, N, K, x32, act) in table[shapes]:
         A = torch.randn(M, K, device=dev).half(); B = torch.randn(N, K, device=dev).half() * (K ** -0.5); bias = torch.randn(N, device=dev)
         C = torch.empty(M, N, device=dev, dtype=torch.float16); X = torch.zeros(M, N, device=dev)
         st = torch.cuda.Stream(dev)
         iters = 20
 
         def call():
-            _lib.check(L.d2s_debug_gemm(A.data_ptr(), B.data_ptr(), bias.data_ptr(), None if x32 else C.data_ptr(), M, N, K, 0,
+            _lib.check(L.d2s_debug_gemm(A.data_ptr(), B.data_ptr(), bias.data_ptr(), None if x32 else C.data_ptr(), M, N, K, act,
                                         X.data_ptr() if x32 else None, torch.cuda.current_stream(dev).cuda_stream))
         with torch.cuda.stream(st):
             for _ in range(3):
@@ -415,78 +697,6 @@ def build_engine(variant, rank, world, dev):
     blob, cfg_json = sharding.broadcast_weights(blob, cfg_json, src=0, device=dev)
     cfg = config_from_hf(DepthAnythingConfig.from_dict(json.loads(cfg_json)))
     return B200Engine(blob, cfg, dev, out_dtype=torch.float16), cfg
-
-
-def run_large4k(args):
-    """configs[2]: DA-V2-Large, 8 x 4K frames per engine call -> 8 Full-SBS frames.  Extra measurement (M = 6224 token rows is
-    where the tcgen05 GEMM is tensor-bound rather than latency-bound); one step = one batch of 8 frames."""
-    import numpy as np
-    import torch
-    from desktop2stereo_b200 import _lib
-    from desktop2stereo_b200.prepost import PostProcessor, preprocess, process
-    from desktop2stereo_b200.stereo import make_sbs_core
-    variant, h, w, B, desc = WORKLOADS["large4k"]
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    engine, cfg = build_engine(variant, 0, 1, dev)
-    L = _lib.lib()
-    g = torch.Generator(device=dev).manual_seed(SEED)
-    RING = 2                                   # 2 x 8 x 33 MB = 531 MB of distinct frames > L2
-    frames = [[torch.randint(0, 256, (h, w, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(B)] for _ in range(RING)]
-    posts = [PostProcessor() for _ in range(B)]    # 8 concurrent streams: one EMA state each
-    batch = torch.empty((B, 3, 294, 518), dtype=torch.float32, device=dev)
-    outs = [torch.empty((h, 2 * w, 3), dtype=torch.float32, device=dev) for _ in range(B)]
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    trace = []
-
-    def step(i):
-        fr = frames[i % RING]
-        e = [ev() for _ in range(4)]
-        e[0].record()
-        rgbs = [process(f, h) for f in fr]
-        for b, rgb in enumerate(rgbs):
-            preprocess(rgb, 518, 14, out=batch[b:b + 1])
-        e[1].record()
-        raw = engine(batch)
-        e[2].record()
-        for b in range(B):
-            d = posts[b](raw[b], out_size=(h, w))
-            make_sbs_core(rgbs[b], d, depth_ratio=DEPTH_RATIO, display_mode=DISPLAY_MODE, out_layout="HWC", out=outs[b])
-        e[3].record()
-        trace.append(e)
-
-    warmup = max(args.warmup, 3)
-    for i in range(warmup):
-        step(i)
-    torch.cuda.synchronize()
-    trace.clear()
-    clocks = ClockSampler(dev.index or 0); clocks.start()
-    l0 = L.d2s_launch_count()
-    s, e = ev(), ev()
-    s.record()
-    for i in range(args.steps):
-        step(i)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e)
-    clk = clocks.stop()
-    st = np.median(np.array([[t[j].elapsed_time(t[j + 1]) for j in range(3)] for t in trace]), 0)
-    peaks, src = load_peaks()
-    gflop = B * model_flops(cfg, 294, 518) / 1e9
-    net_tf = gflop / (st[1] * 1e-3) / 1e3
-    line = {"metric": "end-to-end frames/sec (depth infer + SBS warp)", "value": B * args.steps / (ms / 1e3), "unit": "frames/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
-            "config": {"workload": desc, "l2": "2 batches of 8 distinct 4K frames (531 MB) > 126 MB L2", "parallelism": "one stream, batch of 8 per engine call"},
-            "gpu_launches": int(L.d2s_launch_count() - l0), "clocks": clk,
-            "stage_ms": {"process+preprocess x8": float(st[0]), "engine (batch 8)": float(st[1]), "postprocess+warp x8": float(st[2])},
-            "roofline": {"kernel": "depth network, one graph launch per batch of 8 (ViT-L + DPT on gemm_tc_kernel/tcgen05)", "bound": "tensor",
-                         "achieved": net_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": net_tf / peaks["bf16_tflops_sustained"],
-                         "traffic": None, "peak_source": src, "gflop_per_launch": gflop, "duration_ms": float(st[1])},
-            "roofline_warp": {"kernel": "warp_sbs_fast_kernel x8 (+ postprocess x8)", "bound": "hbm", "bytes_per_launch": h * w * 32,
-                              "note": "stage time covers 8 post-process chains and 8 warp launches"}}
-    print(json.dumps(line))
-    return 0
 
 
 def run_vda1080(args):

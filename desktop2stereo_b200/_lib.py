@@ -61,7 +61,7 @@ class PipeConfig(C.Structure):
                 ("use_temporal_smooth", C.c_int32), ("ema_alpha", C.c_float),
                 ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
                 ("display_mode", C.c_int32), ("fill_16_9", C.c_int32), ("out_dtype", C.c_int32), ("slots", C.c_int32),
-                ("host_io", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("host_io", C.c_int32), ("streams", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 # every symbol include/d2s_b200.h declares: name -> (restype, argtypes)

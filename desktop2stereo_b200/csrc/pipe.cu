@@ -44,6 +44,7 @@ struct d2s_pipe {
     d2s_pipe_config cfg;
     d2s_engine *engine;
     int device;
+    int B;             // video streams per slot = frames per submit (cfg.streams)
     int h, w;          // size of process()'s output (== frame size unless target_height < frame_h)
     int Hm, Wm;        // model input
     int oh, ow;        // packed stereo frame
@@ -59,24 +60,28 @@ namespace d2s {
 
 static size_t dtype_size(int dt) { return dt == D2S_F32 ? 4 : (dt == D2S_U8 ? 1 : 2); }
 
-static void fill_post(const d2s_pipe *p, const PipeSlot &s, d2s_post_params *pp) {
+// b: index of the video stream inside the slot's batch (cfg.streams frames go through the network per submit, one per stream)
+static void fill_post(const d2s_pipe *p, const PipeSlot &s, int b, d2s_post_params *pp) {
     const d2s_pipe_config &c = p->cfg;
     *pp = d2s_post_params{};
-    pp->depth_in = s.plan->out_stage; pp->in_dtype = D2S_F16; pp->H = p->Hm; pp->W = p->Wm;
-    pp->out = s.d_depth; pp->out_dtype = D2S_F16; pp->out_h = p->h; pp->out_w = p->w;
+    pp->depth_in = (const __half *)s.plan->out_stage + (size_t)b * p->Hm * p->Wm; pp->in_dtype = D2S_F16; pp->H = p->Hm; pp->W = p->Wm;
+    pp->out = (__half *)s.d_depth + (size_t)b * p->h * p->w; pp->out_dtype = D2S_F16; pp->out_h = p->h; pp->out_w = p->w;
     pp->compute_dtype = D2S_F16;          // the reference's CUDA path post-processes the autocast (fp16) depth in fp16
     pp->metric = c.metric; pp->percentile = c.percentile; pp->subsample_cap = c.subsample_cap; pp->gamma = c.gamma;
     pp->foreground_scale = c.foreground_scale; pp->aa_strength = c.aa_strength;
-    pp->ema_state = c.use_temporal_smooth ? p->ema_state : nullptr; pp->ema_valid = 2; pp->ema_alpha = c.ema_alpha;
-    pp->workspace = s.ws_post; pp->workspace_bytes = p->ws_post_bytes;
+    pp->ema_state = c.use_temporal_smooth ? (void *)((__half *)p->ema_state + (size_t)b * p->Hm * p->Wm) : nullptr; pp->ema_valid = 2; pp->ema_alpha = c.ema_alpha;
+    pp->workspace = (char *)s.ws_post + (size_t)b * p->ws_post_bytes; pp->workspace_bytes = p->ws_post_bytes;
 }
 
-static void fill_warp(const d2s_pipe *p, const PipeSlot &s, d2s_warp_params *wp) {
+static void *rgb_of(const d2s_pipe *p, const PipeSlot &s, int b) { return (char *)s.d_rgb + (size_t)b * 3 * p->h * p->w * p->rgb_es; }
+static const uint8_t *frame_of(const d2s_pipe *p, const uint8_t *base, int b) { return base + (size_t)b * p->frame_bytes; }
+
+static void fill_warp(const d2s_pipe *p, const PipeSlot &s, int b, d2s_warp_params *wp) {
     const d2s_pipe_config &c = p->cfg;
     *wp = d2s_warp_params{};
-    wp->rgb.base = s.d_rgb; wp->rgb.dtype = c.rgb_dtype; wp->rgb.sc = (int64_t)p->h * p->w; wp->rgb.sy = p->w; wp->rgb.sx = 1;
-    wp->out.base = s.d_out; wp->out.dtype = c.out_dtype; wp->out.sc = 1; wp->out.sy = (int64_t)3 * p->ow; wp->out.sx = 3;
-    wp->depth = s.d_depth; wp->depth_dtype = D2S_F16; wp->depth_h = p->h; wp->depth_w = p->w; wp->h = p->h; wp->w = p->w;
+    wp->rgb.base = rgb_of(p, s, b); wp->rgb.dtype = c.rgb_dtype; wp->rgb.sc = (int64_t)p->h * p->w; wp->rgb.sy = p->w; wp->rgb.sx = 1;
+    wp->out.base = (char *)s.d_out + (size_t)b * p->out_bytes; wp->out.dtype = c.out_dtype; wp->out.sc = 1; wp->out.sy = (int64_t)3 * p->ow; wp->out.sx = 3;
+    wp->depth = (__half *)s.d_depth + (size_t)b * p->h * p->w; wp->depth_dtype = D2S_F16; wp->depth_h = p->h; wp->depth_w = p->w; wp->h = p->h; wp->w = p->w;
     wp->ipd_uv = c.ipd_uv; wp->depth_ratio = c.depth_ratio; wp->convergence = c.convergence;
     wp->display_mode = c.display_mode; wp->fill_16_9 = c.fill_16_9; wp->warp_mode = D2S_WARP_BILINEAR;
     wp->rgb_round_to_depth_dtype = c.rgb_dtype != D2S_F16;   // make_sbs casts rgb to depth.dtype (depth.py:2209-2215)
@@ -101,43 +106,59 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.ema_ev, cudaEventDisableTiming));
     D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.in_ev, cudaEventDisableTiming));
     for (auto &e : s.t) D2S_CHECK_CUDA(cudaEventCreate(&e));
-    D2S_CHECK_CUDA(cudaMalloc((void **)&s.d_frame, p->frame_bytes));
-    D2S_CHECK_CUDA(cudaMalloc(&s.d_rgb, (size_t)3 * p->h * p->w * p->rgb_es));
+    const int B = p->B;
+    D2S_CHECK_CUDA(cudaMalloc((void **)&s.d_frame, B * p->frame_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.d_rgb, (size_t)B * 3 * p->h * p->w * p->rgb_es));
     if (p->ws_proc_bytes) D2S_CHECK_CUDA(cudaMalloc(&s.ws_proc, p->ws_proc_bytes));
     D2S_CHECK_CUDA(cudaMalloc(&s.ws_pre, p->ws_pre_bytes));
-    D2S_CHECK_CUDA(cudaMalloc(&s.ws_post, p->ws_post_bytes));
-    D2S_CHECK_CUDA(cudaMalloc(&s.d_depth, (size_t)p->h * p->w * 2));
-    D2S_CHECK_CUDA(cudaMalloc(&s.d_out, p->out_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.ws_post, B * p->ws_post_bytes));     // (one per stream: its blur-x result waits there for the EMA step)
+    D2S_CHECK_CUDA(cudaMalloc(&s.d_depth, (size_t)B * p->h * p->w * 2));
+    D2S_CHECK_CUDA(cudaMalloc(&s.d_out, B * p->out_bytes));
     if (c.host_io) {
-        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_in, p->frame_bytes, cudaHostAllocDefault));
-        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_out, p->out_bytes, cudaHostAllocDefault));
+        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_in, B * p->frame_bytes, cudaHostAllocDefault));
+        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_out, B * p->out_bytes, cudaHostAllocDefault));
     }
-    TRY_RC(engine_plan(p->engine, 1, p->Hm, p->Wm, D2S_F16, D2S_F16, s.stream, &s.plan));
+    TRY_RC(engine_plan(p->engine, B, p->Hm, p->Wm, D2S_F16, D2S_F16, s.stream, &s.plan));
 
-    // input-independent tables of the two antialias resizes: once, here
-    d2s_image src{};
-    src.base = s.d_rgb; src.dtype = c.rgb_dtype; src.sc = (int64_t)p->h * p->w; src.sy = p->w; src.sx = 1;
+    // input-independent tables of the two antialias resizes: once, here (the workspaces are shared by the slot's streams: the
+    // kernels of one slot run in stream order)
+    auto rgb_view = [&](int b) {
+        d2s_image v{};
+        v.base = rgb_of(p, s, b); v.dtype = c.rgb_dtype; v.sc = (int64_t)p->h * p->w; v.sy = p->w; v.sx = 1;
+        return v;
+    };
+    auto model_in = [&](int b) { return (void *)((__half *)s.plan->in_stage + (size_t)b * 3 * p->Hm * p->Wm); };
+    d2s_image src0 = rgb_view(0);
     TRY_RC(process_phases(s.d_frame, c.frame_h, c.frame_w, c.channels, s.d_rgb, c.rgb_dtype, p->h, p->w, s.ws_proc, p->ws_proc_bytes, 1, s.stream));
-    TRY_RC(preprocess_phases(&src, p->h, p->w, s.plan->in_stage, D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 1, s.stream));
+    TRY_RC(preprocess_phases(&src0, p->h, p->w, model_in(0), D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 1, s.stream));
     D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
 
-    d2s_post_params pp; fill_post(p, s, &pp);
-    d2s_warp_params wp; fill_warp(p, s, &wp);
     const bool split = c.use_temporal_smooth != 0;
     // graph A
     long long k0 = g_launch_count.load();
     TRY_RC(capture_begin(s.stream));
-    int rc = preprocess_phases(&src, p->h, p->w, s.plan->in_stage, D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 2, s.stream);
+    int rc = D2S_OK;
+    for (int b = 0; b < B && !rc; ++b) {
+        d2s_image src = rgb_view(b);
+        rc = preprocess_phases(&src, p->h, p->w, model_in(b), D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 2, s.stream);
+    }
     if (!rc) rc = engine_run_ops(s.plan, s.stream);
-    if (!rc) rc = postprocess_phases(&pp, split ? POST_PHASE_HEAD : POST_PHASE_ALL, s.stream);
-    if (!rc && !split) rc = d2s_make_sbs(&wp, s.stream);
+    for (int b = 0; b < B && !rc; ++b) {
+        d2s_post_params pp; fill_post(p, s, b, &pp);
+        rc = postprocess_phases(&pp, split ? POST_PHASE_HEAD : POST_PHASE_ALL, s.stream);
+        if (!rc && !split) { d2s_warp_params wp; fill_warp(p, s, b, &wp); rc = d2s_make_sbs(&wp, s.stream); }
+    }
     TRY_RC(capture_end(s.stream, rc, &s.graphA, &s.gA));
     s.kernels_a = g_launch_count.load() - k0;
     if (split) {
         k0 = g_launch_count.load();
         TRY_RC(capture_begin(s.stream));
-        rc = postprocess_phases(&pp, POST_PHASE_UP, s.stream);
-        if (!rc) rc = d2s_make_sbs(&wp, s.stream);
+        for (int b = 0; b < B && !rc; ++b) {
+            d2s_post_params pp; fill_post(p, s, b, &pp);
+            d2s_warp_params wp; fill_warp(p, s, b, &wp);
+            rc = postprocess_phases(&pp, POST_PHASE_UP, s.stream);
+            if (!rc) rc = d2s_make_sbs(&wp, s.stream);
+        }
         TRY_RC(capture_end(s.stream, rc, &s.graphB, &s.gB));
         s.kernels_b = g_launch_count.load() - k0;
     }
@@ -170,9 +191,11 @@ extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2
     D2S_REQUIRE(cfg->depth_resolution > 0 && cfg->patch == engine->cfg.patch, "d2s_pipe_create: depth_resolution %d / patch %d", cfg->depth_resolution, cfg->patch);
     // a temporal engine keeps ONE video's window per stream: frames of that video cannot be spread over several slots
     D2S_REQUIRE(!engine->cfg.temporal || cfg->slots == 1, "d2s_pipe_create: a temporal (Video-Depth-Anything) engine needs slots == 1 (its frames are sequential; run one pipe per video)");
+    D2S_REQUIRE(cfg->streams >= 0 && cfg->streams <= 64 && (!engine->cfg.temporal || cfg->streams <= 1), "d2s_pipe_create: streams=%d (1..64; 1 for a temporal engine)", cfg->streams);
     D2S_CHECK_CUDA(cudaSetDevice(engine->device));
     d2s_pipe *p = new d2s_pipe();
     p->cfg = *cfg; p->engine = engine; p->device = engine->device;
+    p->B = cfg->streams > 0 ? cfg->streams : 1;
     if (cfg->target_height >= cfg->frame_h) { p->h = cfg->frame_h; p->w = cfg->frame_w; }
     else {   // depth.py:555-559
         p->h = (cfg->target_height / 2) * 2;
@@ -188,8 +211,8 @@ extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2
     p->ws_pre_bytes = d2s_preprocess_workspace_bytes(p->h, p->w, p->Hm, p->Wm);
     p->ws_post_bytes = d2s_postprocess_workspace_bytes(p->Hm, p->Wm);
     rc = [&]() -> int {
-        D2S_CHECK_CUDA(cudaMalloc(&p->ema_state, (size_t)p->Hm * p->Wm * 2));
-        D2S_CHECK_CUDA(cudaMemset(p->ema_state, 0xFF, (size_t)p->Hm * p->Wm * 2));
+        D2S_CHECK_CUDA(cudaMalloc(&p->ema_state, (size_t)p->B * p->Hm * p->Wm * 2));      // one DepthStabilizer state per stream
+        D2S_CHECK_CUDA(cudaMemset(p->ema_state, 0xFF, (size_t)p->B * p->Hm * p->Wm * 2));
         // several frames in flight share the GPU: the throughput tile policy (d2s_set_policy); one frame alone: latency
         const int old_policy = engine->policy;
         { std::unique_lock<std::mutex> lock(engine->mu); engine->policy = cfg->slots > 1 ? D2S_POLICY_THROUGHPUT : D2S_POLICY_LATENCY; }
@@ -248,18 +271,21 @@ extern "C" int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d
     if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[0], st));
     const uint8_t *src;
     if (c.host_io) {
-        D2S_CHECK_CUDA(cudaMemcpyAsync(s.d_frame, frame ? frame : s.h_in, p->frame_bytes, cudaMemcpyHostToDevice, st));
+        D2S_CHECK_CUDA(cudaMemcpyAsync(s.d_frame, frame ? frame : s.h_in, p->B * p->frame_bytes, cudaMemcpyHostToDevice, st));
         src = s.d_frame;
     } else src = frame ? (const uint8_t *)frame : s.d_frame;
-    int rc = process_phases(src, c.frame_h, c.frame_w, c.channels, s.d_rgb, c.rgb_dtype, p->h, p->w, s.ws_proc, p->ws_proc_bytes, 2, st);
-    if (rc) return rc;
+    int rc = D2S_OK;
+    for (int b = 0; b < p->B; ++b)
+        if ((rc = process_phases(frame_of(p, src, b), c.frame_h, c.frame_w, c.channels, rgb_of(p, s, b), c.rgb_dtype, p->h, p->w, s.ws_proc, p->ws_proc_bytes, 2, st))) return rc;
     if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[1], st));
     D2S_CHECK_CUDA(cudaGraphLaunch(s.gA, st));
     long long kernels = s.kernels_a;
     if (s.gB) {
         if (p->last_ema && p->last_ema != s.ema_ev) D2S_CHECK_CUDA(cudaStreamWaitEvent(st, p->last_ema, 0));
-        d2s_post_params pp; fill_post(p, s, &pp);
-        if ((rc = postprocess_phases(&pp, POST_PHASE_EMA, st))) return rc;
+        for (int b = 0; b < p->B; ++b) {
+            d2s_post_params pp; fill_post(p, s, b, &pp);
+            if ((rc = postprocess_phases(&pp, POST_PHASE_EMA, st))) return rc;
+        }
         D2S_CHECK_CUDA(cudaEventRecord(s.ema_ev, st));
         p->last_ema = s.ema_ev;
         if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[2], st));
@@ -268,7 +294,7 @@ extern "C" int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d
     }
     g_launch_count.fetch_add(kernels, std::memory_order_relaxed);
     if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[3], st));
-    if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, p->out_bytes, cudaMemcpyDeviceToHost, st));
+    if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, p->B * p->out_bytes, cudaMemcpyDeviceToHost, st));
     D2S_CHECK_CUDA(cudaEventRecord(s.done, st));
     s.busy = true;
     return D2S_OK;
@@ -307,7 +333,7 @@ extern "C" int d2s_pipe_slot_times(d2s_pipe_handle p, int slot, float ms[3]) {
 extern "C" int d2s_pipe_reset(d2s_pipe_handle p) {
     D2S_REQUIRE(p != nullptr, "d2s_pipe_reset: null pipe");
     for (auto &s : p->slots) D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
-    D2S_CHECK_CUDA(cudaMemset(p->ema_state, 0xFF, (size_t)p->Hm * p->Wm * 2));
+    D2S_CHECK_CUDA(cudaMemset(p->ema_state, 0xFF, (size_t)p->B * p->Hm * p->Wm * 2));
     p->last_ema = nullptr;
     if (p->engine->cfg.temporal)
         for (auto &s : p->slots) { int rc = d2s_reset_stream(p->engine, s.stream); if (rc) return rc; }

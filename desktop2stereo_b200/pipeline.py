@@ -52,6 +52,7 @@ class _Pipe:
         c.ipd_uv, c.depth_ratio, c.convergence = float(p["ipd_uv"]), float(p["depth_ratio"]), float(p["convergence"])
         c.display_mode, c.fill_16_9 = DISPLAY_MODES[p["display_mode"]], int(bool(p["fill_16_9"]))
         c.out_dtype, c.slots, c.host_io = _TORCH2D2S[owner.out_dtype], owner.n_slots, int(host_io)
+        c.streams = B = owner.streams
         self.handle = C.c_void_p()
         self.device, self.host_io, self.L = owner.device, host_io, L
         with torch.cuda.device(self.device):
@@ -67,12 +68,13 @@ class _Pipe:
             ptr = [C.c_void_p() for _ in range(6)]
             _lib.check(L.d2s_pipe_slot_buffers(self.handle, i, *[C.byref(x) for x in ptr]), "d2s_pipe_slot_buffers")
             hin, hout, _din, dout, ddep, st = [x.value for x in ptr]
+            lead = (B,) if B > 1 else ()       # several streams: one frame of each per submit, stacked on a leading axis
             if host_io:   # numpy views of the library's pinned buffers (no copy)
-                self.host_in.append(np.ctypeslib.as_array((C.c_uint8 * fb.value).from_address(hin)).reshape(h0, w0, ch))
-                raw = np.ctypeslib.as_array((C.c_uint8 * ob.value).from_address(hout))
-                self.host_out.append(raw.view(_NP_OF[odt]).reshape(self.oh, self.ow, 3))
-            self.dev_out.append(_device_view(dout, (self.oh, self.ow, 3), odt, self.device))
-            self.dev_depth.append(_device_view(ddep, (self.h, self.w), torch.float16, self.device))
+                self.host_in.append(np.ctypeslib.as_array((C.c_uint8 * (B * fb.value)).from_address(hin)).reshape(lead + (h0, w0, ch)))
+                raw = np.ctypeslib.as_array((C.c_uint8 * (B * ob.value)).from_address(hout))
+                self.host_out.append(raw.view(_NP_OF[odt]).reshape(lead + (self.oh, self.ow, 3)))
+            self.dev_out.append(_device_view(dout, lead + (self.oh, self.ow, 3), odt, self.device))
+            self.dev_depth.append(_device_view(ddep, lead + (self.h, self.w), torch.float16, self.device))
             self.streams.append(st)
 
     def close(self):
@@ -97,9 +99,11 @@ def _device_view(ptr, shape, dtype, device):
 
 class StereoPipeline:
     def __init__(self, depth_slots: int = 3, display_mode="Full-SBS", ipd_uv=0.064, depth_ratio=2.0, convergence=0.0,
-                 fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None):
+                 fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None, streams=1):
         """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and the post-process settings live there).
-        A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224)."""
+        A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224).
+        streams > 1: that many concurrent video streams share the pipeline; every submit takes one frame of each, stacked as
+        [streams, h, w, ch] (the network runs them as one batch; each stream has its own DepthStabilizer state)."""
         d2s_depth._need_init()
         engine = d2s_depth.model_wraper.model
         if getattr(engine.cfg, "temporal", 0) and depth_slots != 1:
@@ -108,7 +112,7 @@ class StereoPipeline:
         if display_mode not in DISPLAY_MODES:
             raise ValueError(f"display_mode {display_mode!r}")
         self.device = d2s_depth.model_wraper.device if device is None else torch.device(device)
-        self.n_slots = depth_slots
+        self.n_slots, self.streams = depth_slots, int(streams)
         self.params = dict(ipd_uv=ipd_uv, depth_ratio=depth_ratio, convergence=convergence, fill_16_9=fill_16_9,
                            display_mode=display_mode)
         self.use_temporal_smooth, self.out_dtype, self.target_height = use_temporal_smooth, out_dtype, target_height
@@ -123,6 +127,10 @@ class StereoPipeline:
         key = (tuple(shape), bool(host_io))
         p = self._pipes.get(key)
         if p is None:
+            if self.streams > 1:
+                if len(shape) != 4 or shape[0] != self.streams:
+                    raise ValueError(f"expected [streams={self.streams}, h, w, 3|4] frames, got shape {tuple(shape)}")
+                shape = shape[1:]
             if len(shape) != 3 or shape[2] not in (3, 4):
                 raise ValueError(f"expected a uint8 [h,w,3|4] frame, got shape {tuple(shape)}")
             p = self._pipes[key] = _Pipe(self, shape[0], shape[1], shape[2], host_io)

@@ -50,3 +50,54 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _parse_cpulist(text: str) -> list[int]:
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index: int, local_rank: int = 0, local_world: int = 1) -> dict:
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated, so that
+    the per-frame staging buffers (first-touch) and the threads that fill them are local to the GPU's PCIe root.  Round 1 ran all
+    8 ranks on NUMA node 0 (cores 0-31) and the 49.8 MB/frame device->host copies of 8 GPUs converged on one memory controller
+    (SCALE_r01: e2e 0.24x at 8 GPUs).  When several ranks share a node its cores are split between them.
+    Returns what was done (for the bench line); never raises — a container without sysfs/NUMA just stays unbound."""
+    import os
+    info = {"bound": False}
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info.update(pci=bus, numa_node=node)
+        if node < 0:
+            return info
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return info
+        # ranks whose GPUs share this node take disjoint slices of its cores
+        peers = []
+        for r in range(local_world):
+            try:
+                pr = torch.cuda.get_device_properties(r)
+                b = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                if int(open(f"/sys/bus/pci/devices/{b}/numa_node").read()) == node:
+                    peers.append(r)
+            except Exception:
+                pass
+        if local_rank in peers and len(peers) > 1 and len(allowed) >= len(peers):
+            k = len(allowed) // len(peers)
+            i = peers.index(local_rank)
+            allowed = allowed[i * k:(i + 1) * k]
+        os.sched_setaffinity(0, allowed)
+        info.update(bound=True, cpus=len(allowed), first_cpu=allowed[0])
+    except Exception as e:      # no sysfs, no NUMA, restricted cpuset ...
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

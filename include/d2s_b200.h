@@ -202,10 +202,14 @@ typedef struct d2s_pipe_config {
     int32_t out_dtype;            /* packed frame [oh, ow, 3] HWC: D2S_F32 = what make_sbs returns (depth.py:2231), D2S_U8, D2S_F16 */
     int32_t slots;                /* frames in flight (1..64); > 1 builds throughput-policy plans */
     int32_t host_io;              /* 1: frames come from and results go to pinned HOST memory (H2D / D2H copies on the slot's stream) */
-    int32_t reserved[3];
+    int32_t streams;              /* concurrent video streams sharing the pipe (0/1: one).  One submit takes ONE frame of EVERY stream:
+                                     `frame` is [streams][frame_h, frame_w, channels], the result [streams][oh, ow, 3]; the network runs
+                                     them as one batch (BASELINE configs 3/5: 8 x 4K), each stream keeps its own DepthStabilizer state */
+    int32_t reserved[2];
 } d2s_pipe_config;
 int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2s_pipe_handle *out);
 int d2s_pipe_destroy(d2s_pipe_handle p);
+/* frame_bytes / out_bytes are per stream (one frame); a slot's buffers hold `streams` of them back to back */
 int d2s_pipe_geometry(d2s_pipe_handle p, int *h, int *w, int *model_h, int *model_w, int *out_h, int *out_w, size_t *frame_bytes, size_t *out_bytes);
 /* The slot's own buffers (valid for the life of the pipe): pinned host frame / result (host_io), device frame / result / depth
  * [h,w] fp16 (what predict_depth returns), and its stream. */

@@ -4,6 +4,8 @@ process -> predict_depth -> make_sbs with the branches depth.py takes when IS_CU
 Used only by bench.py's `cpu_baseline` leg and `--impl reference` arm (and tests).  The depth network is HF transformers'
 DepthAnythingForDepthEstimation itself (the reference's own third-party dependency), run under bf16 autocast exactly as
 DepthModelWrapper.__call__ does on CPU (depth.py:661-664, 1763-1781).
+Pinned: tests/test_oracle_cpu_pipeline.py runs the UNMODIFIED reference module (oracle/ref_harness.py) and this port on the same
+frames and weights for 3 consecutive frames (EMA state included), Full- and Half-SBS: the float32 frames are bit-identical.
 """
 from __future__ import annotations
 

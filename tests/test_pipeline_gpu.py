@@ -142,3 +142,26 @@ def test_pipeline_rejects_multi_slot_video_engine(cuda_device):
     want = [depth.make_sbs(depth.process(f, 90), depth.predict_depth(depth.process(f, 90)), display_mode="Half-SBS") for f in frames]
     for g, w_ in zip(got, want):
         assert np.array_equal(g, w_)
+
+
+def test_pipeline_several_streams_per_submit(cuda_device):
+    """streams=3 (BASELINE configs 3/5: several concurrent videos batched through the network): stream b of the batched pipe ==
+    that video alone through a single-stream pipe with the same plan policy, EMA state per stream."""
+    from desktop2stereo_b200 import depth
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    depth.init(make_hf_model("Small", 5, TINY), device=cuda_device, depth_resolution=126)
+    S, T = 3, 6
+    vids = [[synth_frame(1000 * s + t, 180, 320, 4) for t in range(T)] for s in range(S)]
+    pipe = StereoPipeline(depth_slots=2, display_mode="Half-SBS", streams=S)
+    got = [r.copy() for r in pipe.run(iter(np.stack([vids[s][t] for s in range(S)]) for t in range(T)))]
+    assert got[0].shape == (S, 180, 320, 3)
+    pipe.close()
+    for s in range(S):
+        single = StereoPipeline(depth_slots=2, display_mode="Half-SBS")
+        want = [r.copy() for r in single.run(iter(vids[s]))]
+        single.close()
+        for t in range(T):
+            # batched rows run through different GEMM tiles than a batch of one: equal to fp16 rounding of the depth, which
+            # moves a pixel by < 0.01 px (sub-grey-level); EMA state is per stream (a shared state would differ by whole levels)
+            assert np.abs(got[t][s] - want[t]).max() <= 1.0, (s, t)
+            assert np.abs(got[t][s] - want[t]).mean() <= 0.05
