@@ -98,6 +98,7 @@ SYMBOLS = {
     "d2s_debug_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "d2s_debug_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "d2s_debug_force_generic_warp": (C.c_int, [C.c_int]),
     "d2s_last_error": (C.c_char_p, []),
     "d2s_version": (C.c_char_p, []),
 }

@@ -13,10 +13,13 @@
 // (~10x the algorithmic bytes); here each source byte is read from HBM once and each
 // output byte written once.
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
 namespace d2s {
+
+static std::atomic<int> g_force_generic{0};   // d2s_debug_force_generic_warp: tests compare the fast path with the generic kernel
 
 struct WarpK {
     const void *rgb; long long rsc, rsy, rsx;
@@ -258,228 +261,251 @@ __device__ __forceinline__ float stage_value(float v, bool rgb_round) {
     }
     return v;
 }
-template <typename RT, typename DT>
-__device__ __noinline__ float3 taps_global(const RT *rgb, long long rsc, long long rsy, long long rsx, int w, int rgb_round, int iy0, bool two,
-                                           int ix0, float nw, float ne, float sw, float se) {
-    const bool okx1 = ix0 + 1 < w;
-    float o[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const RT *p0 = rgb + ch * rsc + (long long)iy0 * rsy + (long long)ix0 * rsx;
-        float acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0)), rgb_round), nw, 0.f);
-        if (okx1) acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0 + rsx)), rgb_round), ne, acc);
-        if (two) {
-            acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0 + rsy)), rgb_round), sw, acc);
-            if (okx1) acc = __fmaf_rn(stage_value<RT, DT>(to_f32<RT>(__ldg(p0 + rsy + rsx)), rgb_round), se, acc);
-        }
-        o[ch] = acc;
-    }
-    return make_float3(o[0], o[1], o[2]);
-}
-
-// ---- staging: one source row segment -> fp32 plane in shared memory (clamped / rounded exactly like load_rgb) ----
-// 16 bytes of RT -> 16/sizeof(RT) staged floats
-template <typename RT, typename DT> struct StageVec;
-template <typename DT> struct StageVec<__half, DT> {
-    static constexpr int N = 8;
-    static __device__ __forceinline__ void unpack(uint4 raw, bool rgb_round, float *f) {
-        const __half2 lo = __float2half2_rn(0.f), hi = __float2half2_rn(255.f);
-        const __half2 *h = (const __half2 *)&raw;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            // clamp in fp16 (exact: both bounds are fp16 values; rounding to DT afterwards commutes with the clamp)
-            float2 t = __half22float2(__hmin2(__hmax2(h[j], lo), hi));
-            f[2 * j] = rgb_round ? round_to<DT>(t.x) : t.x;
-            f[2 * j + 1] = rgb_round ? round_to<DT>(t.y) : t.y;
-        }
-    }
-};
-template <typename DT> struct StageVec<uint8_t, DT> {
-    static constexpr int N = 16;
-    static __device__ __forceinline__ void unpack(uint4 raw, bool, float *f) {
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            f[4 * j] = (float)(w[j] & 0xffu); f[4 * j + 1] = (float)((w[j] >> 8) & 0xffu);
-            f[4 * j + 2] = (float)((w[j] >> 16) & 0xffu); f[4 * j + 3] = (float)(w[j] >> 24);
-        }
-    }
-};
-template <typename DT> struct StageVec<float, DT> {
-    static constexpr int N = 4;
-    static __device__ __forceinline__ void unpack(uint4 raw, bool rgb_round, float *f) {
-        const float w[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) f[j] = stage_value<float, DT>(w[j], rgb_round);
-    }
-};
-template <typename DT> struct StageVec<__nv_bfloat16, DT> {
-    static constexpr int N = 8;
-    static __device__ __forceinline__ void unpack(uint4 raw, bool rgb_round, float *f) {
-        const __nv_bfloat16 *h = (const __nv_bfloat16 *)&raw;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = stage_value<__nv_bfloat16, DT>(__bfloat162float(h[j]), rgb_round);
-    }
-};
-
-// NP consecutive depth values with one vector load (pointer aligned to NP * sizeof(DT))
-template <typename DT, int NP> struct alignas(sizeof(DT) * NP <= 16 ? sizeof(DT) * NP : 16) DepthPack { DT v[NP]; };
-
-// One warped eye pixel straight from global memory: the rare cases the staged window cannot serve (a tap outside the window =
-// depth outside [0,1], or a coordinate that needs grid_sample's reflection).  Same arithmetic as eye_pixel().
-template <typename RT, typename DT>
-__device__ __noinline__ float3 slow_eye(const RT *rgb, long long rsc, long long rsy, long long rsx, int w, int rgb_round, int iy0, float wy0, float wy1,
-                                        bool two, float gx) {
-    const float ix = source_index(gx, w);
-    const int ix0 = (int)floorf(ix);
-    const float wx0 = __fsub_rn((float)(ix0 + 1), ix), wx1 = __fsub_rn(ix, (float)ix0);
-    return taps_global<RT, DT>(rgb, rsc, rsy, rsx, w, rgb_round, iy0, two, ix0, __fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1),
-                               __fmul_rn(wx1, wy1));
-}
-
 __device__ __forceinline__ float clamp255(float v) { return fminf(fmaxf(v, 0.f), 255.f); }
-// staged pixel p lives at float4 index p + p/8: one pad slot per 8 pixels keeps both the 8-pixels-per-thread staging stores and
-// the strided tap loads free of shared-memory bank conflicts
-__device__ __forceinline__ int px_slot(int p) { return p + (p >> 3); }
 
-// OL: output layout known at compile time — 0: HWC contiguous (sx = 3, sc = 1), 1: planar CHW (sx = 1)
-// flags: bit 0 = rgb rows may be staged with 16-byte loads, bit 1 = depth rows may be read with vector loads
-template <typename RT, typename DT, typename OT, int HALF, int OL, int THREADS>
-__global__ void __launch_bounds__(THREADS) warp_sbs_fast_kernel(const WarpK k, int margin, int flags) {
-    typedef typename Vec4<OT>::type V;
-    constexpr int NP = HALF ? 8 : 4;                 // source pixels per thread (4 output pixels per eye)
-    constexpr int SEG = THREADS * NP;                // source pixels per block
-    extern __shared__ __align__(16) float4 s_px[];   // [rows(1|2)][pitch4]: staged pixels, (r, g, b, -) as fp32
+// One packed output pixel of the generic path (what warp_sbs_kernel computes per pixel): used by the fast kernel to redo the rare
+// pixels its staged window cannot serve.  k is a __grid_constant__ kernel parameter, so taking its address costs no local copy.
+template <typename RT, typename DT>
+__device__ __noinline__ void generic_out_pixel(const WarpK *kp, int oy, int ox, float *v) {
+    const WarpK &k = *kp;
+    RowCtx rows[2];
+    int cy0 = (k.half && k.tab) ? 2 * oy : oy;
+    int ey0 = (k.tab ? (cy0 >= k.ph ? cy0 - k.ph : cy0) : cy0) - k.top;
+    int cy1 = cy0 + 1;
+    int ey1 = (k.tab ? (cy1 >= k.ph ? cy1 - k.ph : cy1) : cy1) - k.top;
+    rows[0] = make_row(k, min(max(ey0, 0), k.h - 1));
+    rows[1] = (k.half && k.tab) ? make_row(k, min(max(ey1, 0), k.h - 1)) : rows[0];
+    float a[3];
+    if (!k.half) cat_pixel<RT, DT>(k, rows, oy, ox, a);
+    else {
+        float b[3];
+        if (k.tab) { cat_pixel<RT, DT>(k, rows, 2 * oy, ox, a); cat_pixel<RT, DT>(k, rows, 2 * oy + 1, ox, b); }
+        else       { cat_pixel<RT, DT>(k, rows, oy, 2 * ox, a); cat_pixel<RT, DT>(k, rows, oy, 2 * ox + 1, b); }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[c] = __fmul_rn(__fadd_rn(a[c], b[c]), 0.5f);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = clamp255(a[c]);
+}
+
+// ---- bulk (TMA, non-tensor) store of a contiguous shared-memory run to global memory ----
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Fast path v5.  One block = one source row segment of SEG pixels:
+//   1. the rgb window the segment can reach (SEG + 2*margin pixels of 1-2 source rows) is staged in shared memory as
+//      pixel-interleaved fp32 (r,g,b,-), so that a bilinear tap is one LDS.128;
+//   2. thread t produces the output pixels t, t+128, t+256, t+384 of the segment for BOTH eyes (consecutive lanes = consecutive
+//      pixels: tap loads and depth loads are contiguous across a warp, no bank conflicts, no padding) and parks them in a
+//      shared-memory image of the output run;
+//   3. the two output runs (left eye, right eye) of the segment are contiguous in the packed frame: each leaves with bulk
+//      (TMA) stores, i.e. without per-thread address arithmetic and store instructions.
+// Pixels whose taps leave the staged window (depth outside [0,1]) or need grid_sample's reflection are redone through the
+// generic path (generic_out_pixel) before the run is stored.  Same arithmetic, same FMA order as the generic kernel =>
+// bit-identical output (tests compare both against the oracle).
+// OL: 0 = HWC contiguous (sx = 3, sc = 1), 1 = planar CHW (sx = 1).  flags bit 0: rgb rows may be staged with 16-byte loads,
+// bit 2: the output runs may leave with bulk stores.
+constexpr int kFastThreads = 128;
+
+// two neighbouring pixels of one colour plane (pointer aligned to 2 elements), clamped / rounded exactly like load_rgb
+template <typename RT, typename DT> __device__ __forceinline__ float2 load_px2(const RT *p, bool rgb_round);
+template <> __device__ __forceinline__ float2 load_px2<__half, __half>(const __half *p, bool) {
+    const uint32_t raw = __ldg((const uint32_t *)p);
+    const __half2 v = __hmin2(__hmax2(*(const __half2 *)&raw, __float2half2_rn(0.f)), __float2half2_rn(255.f));   // clamp in fp16: exact
+    return __half22float2(v);
+}
+template <> __device__ __forceinline__ float2 load_px2<uint8_t, __half>(const uint8_t *p, bool) {
+    const uint16_t raw = __ldg((const uint16_t *)p);
+    return make_float2((float)(raw & 0xffu), (float)(raw >> 8));
+}
+template <> __device__ __forceinline__ float2 load_px2<uint8_t, float>(const uint8_t *p, bool) {
+    const uint16_t raw = __ldg((const uint16_t *)p);
+    return make_float2((float)(raw & 0xffu), (float)(raw >> 8));
+}
+template <> __device__ __forceinline__ float2 load_px2<float, float>(const float *p, bool) {
+    const float2 v = __ldg((const float2 *)p);
+    return make_float2(stage_value<float, float>(v.x, false), stage_value<float, float>(v.y, false));
+}
+
+template <typename OT> __device__ __forceinline__ OT out_value(float v) { return from_f32<OT>(clamp255(v)); }   // final clamp, depth.py:2184
+template <> __device__ __forceinline__ uint8_t out_value<uint8_t>(float v) { return (uint8_t)__float2int_rn(clamp255(v)); }
+
+// step 2 for one thread; TWO: the second source row contributes (block-uniform, so the kernel branches once, not per pixel)
+template <typename DT, typename OT, int HALF, int OL, bool TWO>
+__device__ __forceinline__ unsigned fast_pixels(const WarpK &k, const float4 *__restrict__ s0, const float4 *__restrict__ s1, OT *__restrict__ s_out,
+                                                const float *dv, const RowCtx &row, int seg0, int lo, int tw, int tid) {
+    constexpr int THREADS = kFastThreads, OPX = 4, OSEG = THREADS * OPX;
+    const float span = (float)(k.w - 1);
+    const unsigned last_ok = (unsigned)(tw - 1);     // window index a is usable iff 0 <= a and a + 1 <= tw - 1
+    unsigned bad = 0;                                // bit (2*j + e): output pixel j of eye e must be redone by the generic path
+#pragma unroll
+    for (int j = 0; j < OPX; ++j) {
+        const int q = j * THREADS + tid;             // output pixel inside the segment
+        float acc[2][3];                             // Half-SBS: the first pixel of the pair, per eye
+#pragma unroll
+        for (int hp = 0; hp < (HALF ? 2 : 1); ++hp) {
+            const int xr = seg0 + (HALF ? 2 * q + hp : q);
+            const int x = min(xr, k.w - 1);
+            // shift chain, depth.py:2143-2147, :2154 (identical to eye_pixel)
+            const float d = round_to<DT>(__fsub_rn(dv[HALF ? 2 * j + hp : j], k.conv));
+            const float inv = round_to<DT>(__fmul_rn(-d, k.ratio));
+            float s = round_to<DT>(__fmul_rn(inv, k.max_px));
+            s = round_to<DT>(__fmul_rn(s, k.strength));
+            const float sn = round_to<DT>(__fmul_rn(s, k.two_over_wm1));
+            const float xs = linspace_pm1(x, k.w, k.xstep, k.xhalf);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                // grid_sampler source index (same operations as source_index(); the reflection case is left to the generic path)
+                const float gx = e ? __fsub_rn(xs, sn) : __fadd_rn(xs, sn);
+                const float in = fabsf(__fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), span));
+                const float ix = fminf(span, in);    // in >= 0
+                const int ix0 = __float2int_rz(ix);  // ix >= 0 after the clip: truncation == floor
+                const float fx0 = (float)ix0;
+                const float wx0 = __fsub_rn(__fadd_rn(fx0, 1.f), ix), wx1 = __fsub_rn(ix, fx0);   // (float)(ix0 + 1) == fx0 + 1 exactly (ix0 < 2^24)
+                // Both taps ix0, ix0 + 1 must lie inside the staged window [lo, lo + tw).  One unsigned compare covers a < 0,
+                // a + 1 >= tw AND the reflection case: in >= span gives ix0 = w - 1, i.e. a >= tw - 1 (the window ends at or before w).
+                const unsigned a = (unsigned)(ix0 - lo);
+                const bool oob = a >= last_ok;
+                const unsigned ac = oob ? 0u : a;
+                const float4 p00 = s0[ac], p01 = s0[ac + 1];
+                const float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
+                float cx = __fmaf_rn(p01.x, ne, __fmaf_rn(p00.x, nw, 0.f));
+                float cy = __fmaf_rn(p01.y, ne, __fmaf_rn(p00.y, nw, 0.f));
+                float cz = __fmaf_rn(p01.z, ne, __fmaf_rn(p00.z, nw, 0.f));
+                if (TWO) {
+                    const float4 p10 = s1[ac], p11 = s1[ac + 1];
+                    const float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
+                    cx = __fmaf_rn(p11.x, se, __fmaf_rn(p10.x, sw, cx));
+                    cy = __fmaf_rn(p11.y, se, __fmaf_rn(p10.y, sw, cy));
+                    cz = __fmaf_rn(p11.z, se, __fmaf_rn(p10.z, sw, cz));
+                }
+                if (oob && xr < k.w) bad |= 1u << (2 * j + e);
+                if (HALF && hp == 0) { acc[e][0] = cx; acc[e][1] = cy; acc[e][2] = cz; continue; }
+                if (HALF) {   // F.interpolate(mode="area") at an exact 2:1 ratio: (a + b) / 2
+                    cx = __fmul_rn(__fadd_rn(acc[e][0], cx), 0.5f); cy = __fmul_rn(__fadd_rn(acc[e][1], cy), 0.5f); cz = __fmul_rn(__fadd_rn(acc[e][2], cz), 0.5f);
+                }
+                OT *o = s_out + e * 3 * OSEG;
+                if (OL == 0) { o[q * 3] = out_value<OT>(cx); o[q * 3 + 1] = out_value<OT>(cy); o[q * 3 + 2] = out_value<OT>(cz); }
+                else { o[q] = out_value<OT>(cx); o[OSEG + q] = out_value<OT>(cy); o[2 * OSEG + q] = out_value<OT>(cz); }
+            }
+        }
+    }
+    return bad;
+}
+
+template <typename RT, typename DT, typename OT, int HALF, int OL>
+__global__ void __launch_bounds__(kFastThreads) warp_sbs_fast_kernel(const __grid_constant__ WarpK k, int margin, int flags) {
+    constexpr int THREADS = kFastThreads;
+    constexpr int OPX = 4;                           // output pixels per thread and eye
+    constexpr int OSEG = THREADS * OPX;              // output pixels per block and eye (512)
+    constexpr int SEG = HALF ? 2 * OSEG : OSEG;      // source pixels per block
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const int pitch4 = SEG + 2 * margin;
+    float4 *s_px = (float4 *)s_raw;                                  // [rows(2)][pitch4]
+    OT *s_out = (OT *)(s_raw + (size_t)2 * pitch4 * sizeof(float4));  // [eye][3 * OSEG] (HWC: q*3+c, planar: c*OSEG+q)
     const int y = blockIdx.y;
     const int seg0 = blockIdx.x * SEG;
-    const int pitch4 = px_slot(SEG + 2 * margin) + 1;
     const int lo = max(seg0 - margin, 0), hi = min(seg0 + SEG + margin, k.w);   // staged source columns [lo, hi); margin % 16 == 0
     const int tw = hi - lo;
     const RowCtx row = make_row(k, y);
     const bool two = row.ok1 && row.wy1 != 0.f;      // second source row contributes (block-uniform)
-    const int nrows = two ? 2 : 1;
-    // the depth values of this thread's pixels: issued first, so that their DRAM round trip overlaps the staging loads
-    const int x0 = seg0 + threadIdx.x * NP;
-    const int npx = min(NP, k.w - x0);               // <= 0: thread beyond the row; < NP only for the last thread of a row
-    DepthPack<DT, NP> pk;
-    const bool dvec = (flags & 2) && npx == NP;
-    if (dvec) pk = *(const DepthPack<DT, NP> *)((const DT *)k.depth + (size_t)y * k.w + x0);
+    const int tid = threadIdx.x;
+    // ---- 0. this thread's depth values: issued first, so that their DRAM round trip overlaps the staging loads
+    float dv[HALF ? 2 * OPX : OPX];
     {
-        typedef StageVec<RT, DT> SV;
-        const bool rr = k.rgb_round;
-        const int nv = (flags & 1) ? tw / SV::N : 0;
-        const RT *src = (const RT *)k.rgb + (long long)row.iy0 * k.rsy + (long long)lo * k.rsx;
-        for (int i = threadIdx.x; i < nv; i += THREADS) {
-            uint4 raw[2][3];                         // every load of both rows in flight before the first use
+        const DT *drow = (const DT *)k.depth + (size_t)y * k.w;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                raw[0][c] = __ldg((const uint4 *)(src + c * k.rsc) + i);
-                if (two) raw[1][c] = __ldg((const uint4 *)(src + k.rsy + c * k.rsc) + i);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (r == 1 && !two) break;
-                float f0[SV::N], f1[SV::N], f2[SV::N];
-                SV::unpack(raw[r][0], rr, f0); SV::unpack(raw[r][1], rr, f1); SV::unpack(raw[r][2], rr, f2);
-                float4 *dst = s_px + r * pitch4;
-#pragma unroll
-                for (int j = 0; j < SV::N; ++j) dst[px_slot(i * SV::N + j)] = make_float4(f0[j], f1[j], f2[j], 0.f);
+        for (int j = 0; j < OPX; ++j) {
+            const int q = j * THREADS + tid;
+            if (!HALF) {
+                const int x = min(seg0 + q, k.w - 1);
+                dv[j] = k.lowres ? load_depth<DT>(k, y, x) : to_f32<DT>(__ldg(drow + x));
+            } else {
+                const int x = min(seg0 + 2 * q, k.w - 2);              // w is even on this path
+                dv[2 * j] = k.lowres ? load_depth<DT>(k, y, x) : to_f32<DT>(__ldg(drow + x));
+                dv[2 * j + 1] = k.lowres ? load_depth<DT>(k, y, x + 1) : to_f32<DT>(__ldg(drow + x + 1));
             }
         }
-        for (int r = 0; r < nrows; ++r) {
+    }
+    // ---- 1. staging: a thread converts TWO neighbouring pixels per step (one 2-pixel load per colour plane), so that a warp's
+    //         16-byte shared-memory stores are (almost) contiguous — wider per-thread loads make those stores collide 8-way, and
+    //         every warp of the block waits for them at the barrier below
+    {
+        const bool rr = k.rgb_round;
+        const int np2 = (flags & 1) ? tw / 2 : 0;
+        const RT *src = (const RT *)k.rgb + (long long)row.iy0 * k.rsy + (long long)lo * k.rsx;
+        for (int r = 0; r < (two ? 2 : 1); ++r) {
             float4 *dst = s_px + r * pitch4;
-            for (int x = nv * SV::N + threadIdx.x; x < tw; x += THREADS) {
-                const RT *p = src + r * k.rsy + (long long)x * k.rsx;
-                dst[px_slot(x)] = make_float4(stage_value<RT, DT>(to_f32<RT>(__ldg(p)), rr), stage_value<RT, DT>(to_f32<RT>(__ldg(p + k.rsc)), rr),
-                                              stage_value<RT, DT>(to_f32<RT>(__ldg(p + 2 * k.rsc)), rr), 0.f);
+            const RT *srow = src + r * k.rsy;
+            for (int i = tid; i < np2; i += THREADS) {
+                float2 c0 = load_px2<RT, DT>(srow + 2 * i, rr), c1 = load_px2<RT, DT>(srow + k.rsc + 2 * i, rr), c2 = load_px2<RT, DT>(srow + 2 * k.rsc + 2 * i, rr);
+                dst[2 * i] = make_float4(c0.x, c1.x, c2.x, 0.f);
+                dst[2 * i + 1] = make_float4(c0.y, c1.y, c2.y, 0.f);
+            }
+            for (int x = 2 * np2 + tid; x < tw; x += THREADS) {
+                const RT *p = srow + (long long)x * k.rsx;
+                dst[x] = make_float4(stage_value<RT, DT>(to_f32<RT>(__ldg(p)), rr), stage_value<RT, DT>(to_f32<RT>(__ldg(p + k.rsc)), rr),
+                                     stage_value<RT, DT>(to_f32<RT>(__ldg(p + 2 * k.rsc)), rr), 0.f);
             }
         }
     }
     __syncthreads();
-    if (x0 >= k.w) return;
-    const float4 *s0 = s_px, *s1 = s_px + pitch4;
-
-    float dv[NP];
-    if (dvec) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) dv[p] = to_f32<DT>(pk.v[p]);
-    } else {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) dv[p] = load_depth<DT>(k, y, min(x0 + p, k.w - 1));   // clamped duplicates are never stored
-    }
-
-    const float span = (float)(k.w - 1);
-    float v[2][4][3];                                // [eye][output pixel][channel]
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        const int x = min(x0 + p, k.w - 1);
-        // shift chain, depth.py:2143-2147, :2154 (identical to eye_pixel)
-        float d = round_to<DT>(__fsub_rn(dv[p], k.conv));
-        float inv = round_to<DT>(__fmul_rn(-d, k.ratio));
-        float s = round_to<DT>(__fmul_rn(inv, k.max_px));
-        s = round_to<DT>(__fmul_rn(s, k.strength));
-        const float sn = round_to<DT>(__fmul_rn(s, k.two_over_wm1));
-        const float xs = linspace_pm1(x, k.w, k.xstep, k.xhalf);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            // grid_sampler source index (same operations as source_index(); the reflection case is left to slow_eye)
-            const float gx = e ? __fsub_rn(xs, sn) : __fadd_rn(xs, sn);
-            const float in = fabsf(__fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), span));
-            const float ix = fminf(span, fmaxf(in, 0.f));
-            const int ix0 = __float2int_rz(ix);      // ix >= 0 after the clip: truncation == floor
-            const float fx0 = (float)ix0;
-            const float wx0 = __fsub_rn(__fadd_rn(fx0, 1.f), ix), wx1 = __fsub_rn(ix, fx0);   // (float)(ix0 + 1) == fx0 + 1 exactly (ix0 < 2^24)
-            const int a = ix0 - lo, b = a + (ix0 + 1 < k.w ? 1 : 0);
-            // the east taps are taken unconditionally: when ix0 + 1 == w their weights are exactly 0 (ix == ix0 after the clip)
-            const int ia = px_slot(min(max(a, 0), tw - 1)), ib = px_slot(min(max(b, 0), tw - 1));
-            const float4 p00 = s0[ia], p01 = s0[ib];
-            const float nw = __fmul_rn(wx0, row.wy0), ne = __fmul_rn(wx1, row.wy0);
-            float3 c;
-            c.x = __fmaf_rn(p01.x, ne, __fmaf_rn(p00.x, nw, 0.f));
-            c.y = __fmaf_rn(p01.y, ne, __fmaf_rn(p00.y, nw, 0.f));
-            c.z = __fmaf_rn(p01.z, ne, __fmaf_rn(p00.z, nw, 0.f));
-            if (two) {
-                const float4 p10 = s1[ia], p11 = s1[ib];
-                const float sw = __fmul_rn(wx0, row.wy1), se = __fmul_rn(wx1, row.wy1);
-                c.x = __fmaf_rn(p11.x, se, __fmaf_rn(p10.x, sw, c.x));
-                c.y = __fmaf_rn(p11.y, se, __fmaf_rn(p10.y, sw, c.y));
-                c.z = __fmaf_rn(p11.z, se, __fmaf_rn(p10.z, sw, c.z));
-            }
-            if (in >= span || a < 0 || b >= tw)      // rare: outside the staged window, or a coordinate grid_sample would reflect
-                c = slow_eye<RT, DT>((const RT *)k.rgb, k.rsc, k.rsy, k.rsx, k.w, k.rgb_round, row.iy0, row.wy0, row.wy1, two, gx);
-            if (!HALF) {
-                v[e][p & 3][0] = clamp255(c.x); v[e][p & 3][1] = clamp255(c.y); v[e][p & 3][2] = clamp255(c.z);   // final clamp, depth.py:2184
-            } else if ((p & 1) == 0) {
-                v[e][p >> 1][0] = c.x; v[e][p >> 1][1] = c.y; v[e][p >> 1][2] = c.z;
-            } else {   // F.interpolate(mode="area") at an exact 2:1 ratio: (a + b) / 2, then the final clamp
-                v[e][p >> 1][0] = clamp255(__fmul_rn(__fadd_rn(v[e][p >> 1][0], c.x), 0.5f));
-                v[e][p >> 1][1] = clamp255(__fmul_rn(__fadd_rn(v[e][p >> 1][1], c.y), 0.5f));
-                v[e][p >> 1][2] = clamp255(__fmul_rn(__fadd_rn(v[e][p >> 1][2], c.z), 0.5f));
-            }
+    const int nsrc = min(SEG, k.w - seg0);           // valid source pixels of this segment
+    const int nout = HALF ? nsrc / 2 : nsrc;         // valid output pixels per eye
+    // ---- 2. both eyes of this thread's pixels -> s_out
+    const unsigned bad = two ? fast_pixels<DT, OT, HALF, OL, true>(k, s_px, s_px + pitch4, s_out, dv, row, seg0, lo, tw, tid)
+                             : fast_pixels<DT, OT, HALF, OL, false>(k, s_px, s_px + pitch4, s_out, dv, row, seg0, lo, tw, tid);
+    // ---- 2b. the rare pixels the staged window could not serve: generic path
+    if (bad) {
+#pragma unroll 1
+        for (int b = 0; b < 2 * OPX; ++b) {
+            if (!((bad >> b) & 1u)) continue;
+            const int j = b >> 1, e = b & 1, q = j * THREADS + tid;
+            if (q >= nout) continue;
+            const int oy = k.tab ? e * k.h + y : y;
+            const int ox = (k.tab ? 0 : e * (HALF ? k.w / 2 : k.w)) + (HALF ? seg0 / 2 : seg0) + q;
+            float v[3];
+            generic_out_pixel<RT, DT>(&k, oy, ox, v);
+            OT *o = s_out + e * 3 * OSEG;
+            if (OL == 0) { o[q * 3] = from_f32<OT>(v[0]); o[q * 3 + 1] = from_f32<OT>(v[1]); o[q * 3 + 2] = from_f32<OT>(v[2]); }
+            else { o[q] = from_f32<OT>(v[0]); o[OSEG + q] = from_f32<OT>(v[1]); o[2 * OSEG + q] = from_f32<OT>(v[2]); }
         }
     }
+    // ---- 3. the output runs leave
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of s_out -> visible to the bulk-copy engine
+    __syncthreads();
+    const int ox0 = HALF ? seg0 / 2 : seg0;
+    const bool bulk = (flags & 4) != 0 && ((nout * (int)sizeof(OT)) % 16) == 0;   // flags bit 2: every run start is 16-byte aligned
+    if (bulk) {
+        if (tid < 2) {
+            const int e = tid;
+            const int oy = k.tab ? e * k.h + y : y;
+            const int ox = (k.tab ? 0 : e * (HALF ? k.w / 2 : k.w)) + ox0;
+            OT *g = (OT *)k.out + (long long)oy * k.osy + (long long)ox * (OL == 0 ? 3 : 1);
+            const OT *sm = s_out + e * 3 * OSEG;
+            if (OL == 0) bulk_store(g, sm, (uint32_t)(nout * 3 * sizeof(OT)));
+            else {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const int oy = k.tab ? e * k.h + y : y;
-        const int ox = (k.tab ? 0 : e * (HALF ? k.w / 2 : k.w)) + (HALF ? x0 / 2 : x0);
-        const int valid = HALF ? npx / 2 : npx;
-        OT *base = (OT *)k.out + (long long)oy * k.osy + (long long)ox * (OL == 0 ? 3 : 1);
-        if (valid == 4 && ((uintptr_t)base % sizeof(V)) == 0 && (OL == 0 || (k.osc * (long long)sizeof(OT)) % sizeof(V) == 0)) {
-            if (OL == 0) {
-                V *dvp = (V *)base;
-                dvp[0] = Vec4<OT>::pack(v[e][0][0], v[e][0][1], v[e][0][2], v[e][1][0]);
-                dvp[1] = Vec4<OT>::pack(v[e][1][1], v[e][1][2], v[e][2][0], v[e][2][1]);
-                dvp[2] = Vec4<OT>::pack(v[e][2][2], v[e][3][0], v[e][3][1], v[e][3][2]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) *(V *)(base + c * k.osc) = Vec4<OT>::pack(v[e][0][c], v[e][1][c], v[e][2][c], v[e][3][c]);
+                for (int c = 0; c < 3; ++c) bulk_store(g + c * k.osc, sm + c * OSEG, (uint32_t)(nout * sizeof(OT)));
             }
-        } else {
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp)
-#pragma unroll
+            bulk_commit_wait();                      // the run has been READ out of shared memory before the block may exit
+        }
+    } else {
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+            const int oy = k.tab ? e * k.h + y : y;
+            const int ox = (k.tab ? 0 : e * (HALF ? k.w / 2 : k.w)) + ox0;
+            OT *g = (OT *)k.out + (long long)oy * k.osy + (long long)ox * (OL == 0 ? 3 : 1);
+            const OT *sm = s_out + e * 3 * OSEG;
+            if (OL == 0) { for (int i = tid; i < nout * 3; i += THREADS) g[i] = sm[i]; }
+            else {
                 for (int c = 0; c < 3; ++c)
-                    if (pp < valid) base[OL == 0 ? pp * 3 + c : c * k.osc + pp] = from_f32<OT>(v[e][pp][c]);
+                    for (int i = tid; i < nout; i += THREADS) g[c * k.osc + i] = sm[c * OSEG + i];
+            }
         }
     }
 }
@@ -517,23 +543,36 @@ static int launch_depth(const WarpK &k, int depth_dtype, int out_dtype, dim3 gri
 
 template <typename RT, typename DT, typename OT>
 static int launch_fast_t(const WarpK &k, bool half, int margin, d2s_stream_t st) {
-    constexpr int kFull = 128, kHalf = 128;          // threads per block: 512 (Full) / 1024 (Half-SBS) source pixels per block
-    const int seg = half ? 1024 : 512;               // small blocks: while some blocks of an SM wait on their staging loads, others compute
+    const int seg = half ? 1024 : 512;               // source pixels per block (512 output pixels per eye)
     dim3 grid(ceil_div(k.w, seg), k.h);
     const int padded = seg + 2 * margin;
-    size_t smem = (size_t)2 * (padded + (padded >> 3) + 1) * sizeof(float4);
+    const size_t smem = (size_t)2 * padded * sizeof(float4) + (size_t)2 * 3 * 512 * sizeof(OT);
     const bool hwc = k.osx == 3 && k.osc == 1, chw = k.osx == 1;
     if (!hwc && !chw) return -1;
     int flags = 0;
     // 16-byte staging loads: contiguous pixels, every row/plane start 16-byte aligned (lo is a multiple of 8... of 16 for u8)
-    const size_t es = sizeof(RT);
+    const size_t es = sizeof(RT), oes = sizeof(OT);
     if (k.rsx == 1 && ((uintptr_t)k.rgb % 16) == 0 && (k.rsy * (long long)es) % 16 == 0 && (k.rsc * (long long)es) % 16 == 0 && (margin * es) % 16 == 0) flags |= 1;
-    const int np = half ? 8 : 4;
-    if (!k.lowres && k.w % np == 0 && ((uintptr_t)k.depth % 16) == 0) flags |= 2;
-    if (half) { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 0, kHalf>), grid, kHalf, smem, st, k, margin, flags);
-                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 1, kHalf>), grid, kHalf, smem, st, k, margin, flags); }
-    else      { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 0, kFull>), grid, kFull, smem, st, k, margin, flags);
-                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 1, kFull>), grid, kFull, smem, st, k, margin, flags); }
+    // bulk stores: every output run starts 16-byte aligned (base, row pitch, the right eye's offset, the 512-pixel segment pitch;
+    // planar: the plane pitch too)
+    {
+        const long long ew = half ? k.w / 2 : k.w;
+        const long long px = hwc ? 3 : 1;
+        bool ok = ((uintptr_t)k.out % 16) == 0 && (k.osy * (long long)oes) % 16 == 0 && (512 * px * (long long)oes) % 16 == 0 &&
+                  (k.tab || (ew * px * (long long)oes) % 16 == 0) && (hwc || (k.osc * (long long)oes) % 16 == 0);
+        if (ok) flags |= 4;
+    }
+    static std::once_flag once;                      // (one per <RT, DT, OT> instantiation) Half-SBS windows exceed the 48 KB default
+    std::call_once(once, [] {
+        cudaFuncSetAttribute((const void *)warp_sbs_fast_kernel<RT, DT, OT, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute((const void *)warp_sbs_fast_kernel<RT, DT, OT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute((const void *)warp_sbs_fast_kernel<RT, DT, OT, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute((const void *)warp_sbs_fast_kernel<RT, DT, OT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
+    if (half) { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 0>), grid, kFastThreads, smem, st, k, margin, flags);
+                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 1, 1>), grid, kFastThreads, smem, st, k, margin, flags); }
+    else      { if (hwc) D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 0>), grid, kFastThreads, smem, st, k, margin, flags);
+                else     D2S_LAUNCH((warp_sbs_fast_kernel<RT, DT, OT, 0, 1>), grid, kFastThreads, smem, st, k, margin, flags); }
     return D2S_OK;
 }
 // Instantiated for the dtype combinations the pipeline produces; anything else (-1) takes the generic kernel.
@@ -554,6 +593,11 @@ static int launch_fast(const WarpK &k, int rgb_dt, int depth_dt, int out_dt, boo
 }  // namespace d2s
 
 using namespace d2s;
+
+extern "C" int d2s_debug_force_generic_warp(int on) {
+    g_force_generic.store(on ? 1 : 0, std::memory_order_relaxed);
+    return D2S_OK;
+}
 
 extern "C" int d2s_sbs_out_shape(int h, int w, int display_mode, int fill_16_9, int *out_h, int *out_w) {
     D2S_REQUIRE(h > 0 && w > 0 && out_h && out_w, "d2s_sbs_out_shape: bad arguments");
@@ -602,8 +646,7 @@ extern "C" int d2s_make_sbs(const d2s_warp_params *p, d2s_stream_t stream) {
         const bool half_sbs = k.half && !k.tab;
         const double smax = fmax(fabs(0.0 - p->convergence), fabs(1.0 - p->convergence)) * fabs(p->depth_ratio) * fabs(p->ipd_uv * p->w) * 0.05;
         const int margin = ((int)ceil(smax) + 2 + 15) / 16 * 16;   // multiple of 16: staged windows start 16-byte aligned for every dtype
-        const char *nf = getenv("D2S_WARP_GENERIC");
-        if (!(nf && nf[0] == '1') && !k.gather && !p->fill_16_9 && !k.idx_l && !k.idx_r && (!k.half || (half_sbs && k.w % 2 == 0)) && margin <= 128) {
+        if (!g_force_generic.load(std::memory_order_relaxed) && !k.gather && !p->fill_16_9 && !k.idx_l && !k.idx_r && (!k.half || (half_sbs && k.w % 2 == 0)) && margin <= 128) {
             int rc = launch_fast(k, p->rgb.dtype, p->depth_dtype, p->out.dtype, half_sbs, margin, stream);
             if (rc != -1) { if (rc == D2S_OK) D2S_POST_LAUNCH(); return rc; }
         }

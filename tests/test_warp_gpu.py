@@ -148,12 +148,14 @@ def test_make_sbs_host_signature(cuda_device):
     assert b.shape == (h, 2 * w, 3)
 
 
-def test_fast_path_equals_generic_and_oracle(cuda_device, monkeypatch):
+def test_fast_path_equals_generic_and_oracle(cuda_device):
     """The smem-staged source-centric kernel and the generic output-centric kernel are the same function, bit for bit —
     including depth outside [0,1], whose taps leave the staged window and fall back to global loads."""
+    from desktop2stereo_b200 import _lib
     from desktop2stereo_b200.stereo import make_sbs_core
+    force_generic = _lib.lib().d2s_debug_force_generic_warp
     rng = np.random.default_rng(21)
-    for (h, w) in [(1080, 1920), (33, 70), (64, 1030)]:
+    for (h, w) in [(1080, 1920), (33, 70), (64, 1030), (37, 1296)]:
         rgb = rng.integers(0, 256, (3, h, w)).astype(np.uint8)
         for scale, conv, ratio in [(1.0, 0.0, 2.0), (1.0, 0.5, 4.0), (6.0, 0.0, 4.0)]:   # scale 6: depth in [-2.5, 3.5]
             dep = ((rng.random((h, w)).astype(np.float32) - 0.4) * scale).astype(np.float32)
@@ -162,11 +164,16 @@ def test_fast_path_equals_generic_and_oracle(cuda_device, monkeypatch):
                     r = torch.from_numpy(rgb).to(cuda_device)
                     r = r.half() if dt == torch.float16 else r
                     d = torch.from_numpy(dep).to(cuda_device).to(dt)
-                    monkeypatch.delenv("D2S_WARP_GENERIC", raising=False)
+                    for layout, odt in (("CHW", torch.float32), ("HWC", torch.float32), ("HWC", torch.uint8), ("CHW", torch.float16)):
+                        force_generic(0)
+                        fast = make_sbs_core(r, d, 0.064, ratio, mode, False, conv, out_layout=layout, out_dtype=odt)
+                        force_generic(1)
+                        try:
+                            gen = make_sbs_core(r, d, 0.064, ratio, mode, False, conv, out_layout=layout, out_dtype=odt)
+                        finally:
+                            force_generic(0)
+                        assert torch.equal(fast, gen), (h, w, scale, mode, dt, layout, odt)
                     fast = make_sbs_core(r, d, 0.064, ratio, mode, False, conv)
-                    monkeypatch.setenv("D2S_WARP_GENERIC", "1")
-                    gen = make_sbs_core(r, d, 0.064, ratio, mode, False, conv)
-                    assert torch.equal(fast, gen), (h, w, scale, mode, dt)
             if h < 100:
                 o = owarp.make_sbs_core_oracle(rgb.astype(np.float32), d.float().cpu().numpy(), 0.064, ratio, "Half-SBS", False, conv,
                                                depth_dtype="float32")
