@@ -53,6 +53,14 @@ class PostParams(C.Structure):
                 ("ema_alpha", C.c_float), ("out_lowres", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class DibrParams(C.Structure):
+    _fields_ = [("rgb", Image), ("out", Image), ("depth", C.c_void_p), ("depth_dtype", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("display_mode", C.c_int32), ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
+                ("roll", C.c_double), ("resolution_x", C.c_float), ("resolution_y", C.c_float), ("search_radius", C.c_int32),
+                ("depth_tolerance", C.c_float), ("blur_radius", C.c_float), ("feather_enabled", C.c_int32),
+                ("feather_width", C.c_float), ("corner_radius", C.c_float)]
+
+
 class PipeConfig(C.Structure):
     _fields_ = [("frame_h", C.c_int32), ("frame_w", C.c_int32), ("channels", C.c_int32), ("target_height", C.c_int32),
                 ("rgb_dtype", C.c_int32), ("depth_resolution", C.c_int32), ("patch", C.c_int32),
@@ -85,6 +93,8 @@ SYMBOLS = {
     "d2s_postprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "d2s_postprocess": (C.c_int, [C.POINTER(PostParams), C.c_void_p]),
     "d2s_overlay_fps": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_char_p, C.c_void_p]),
+    "d2s_dibr_out_shape": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
+    "d2s_make_sbs_dibr": (C.c_int, [C.POINTER(DibrParams), C.c_void_p]),
     "d2s_pipe_create": (C.c_int, [C.c_void_p, C.POINTER(PipeConfig), C.POINTER(C.c_void_p)]),
     "d2s_pipe_destroy": (C.c_int, [C.c_void_p]),
     "d2s_pipe_geometry": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_size_t)] * 2),

@@ -18,6 +18,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 PER_FILE = {
     "warp.cu": ["-fmad=false"],
     "prepost.cu": ["-fmad=false"],
+    "dibr.cu": ["-fmad=false"],
 }
 
 

@@ -99,6 +99,42 @@ def make_sbs_core(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ra
     return (out, il, ir) if return_indices else out
 
 
+def make_sbs_dibr(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ratio=1.0, convergence=0.0, display_mode="Half-SBS", *,
+                  roll=0.0, resolution=None, search_radius=12, depth_tolerance=0.012, blur_radius=2.5, feather_enabled=False,
+                  feather_width=0.0, corner_radius=0.0, rgb_layout="CHW", out: torch.Tensor | None = None, out_dtype=torch.float32,
+                  out_layout="CHW"):
+    """The reference viewer's occlusion-aware stereo rendering (viewer.py:386-631: disocclusion confidence + push-pull inpaint) as
+    a tensor function: rgb [3,h,w] (0..255) + depth [h,w] -> packed frame [3,oh,ow] (or HWC), both eye views side by side / top-bottom
+    as StereoWindow.render lays them out (viewer.py:2680-2760).  Defaults are the viewer's (ipd 0.064, depth_ratio 1.0, viewer.py:1326).
+    `resolution` = u_resolution (default: the eye view's size)."""
+    _require_cuda(rgb, "rgb"), _require_cuda(depth, "depth")
+    if display_mode not in DISPLAY_MODES:
+        raise ValueError(f"display_mode {display_mode!r}")
+    h, w = rgb.shape[1:] if rgb_layout == "CHW" else rgb.shape[:2]
+    depth = depth.squeeze().contiguous()
+    if depth.dtype not in (torch.float32, torch.float16):
+        depth = depth.float()
+    if tuple(depth.shape) != (h, w):
+        raise ValueError(f"depth must be [{h},{w}], got {tuple(depth.shape)}")
+    L = _lib.lib()
+    g = [C.c_int() for _ in range(4)]
+    _lib.check(L.d2s_dibr_out_shape(h, w, DISPLAY_MODES[display_mode], *[C.byref(x) for x in g]), "d2s_dibr_out_shape")
+    vh, vw, oh, ow = [x.value for x in g]
+    if out is None:
+        out = torch.empty((3, oh, ow) if out_layout == "CHW" else (oh, ow, 3), dtype=out_dtype, device=rgb.device)
+    p = _lib.DibrParams()
+    p.rgb, p.out = image_view(rgb, rgb_layout), image_view(out, out_layout)
+    p.depth, p.depth_dtype, p.h, p.w = depth.data_ptr(), _TORCH2D2S[depth.dtype], h, w
+    p.display_mode = DISPLAY_MODES[display_mode]
+    p.ipd_uv, p.depth_ratio, p.convergence, p.roll = float(ipd_uv), float(depth_ratio), float(convergence), float(roll)
+    p.resolution_x, p.resolution_y = (resolution if resolution is not None else (0.0, 0.0))
+    p.search_radius, p.depth_tolerance, p.blur_radius = int(search_radius), float(depth_tolerance), float(blur_radius)
+    p.feather_enabled, p.feather_width, p.corner_radius = int(bool(feather_enabled)), float(feather_width), float(corner_radius)
+    with torch.cuda.device(rgb.device):
+        _lib.check(L.d2s_make_sbs_dibr(C.byref(p), _stream_ptr(rgb.device)), "d2s_make_sbs_dibr")
+    return out
+
+
 class _PinnedRing:
     """Ring of pinned host buffers for the float32 HWC result of make_sbs (depth.py:767-773).
     A frame handed out stays valid for `depth-1` further calls."""

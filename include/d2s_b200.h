@@ -176,6 +176,33 @@ int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream);
 /* overlay_fps: blends the "FPS: xx.x" glyph mask into an RGB image in place. */
 int d2s_overlay_fps(const d2s_image *rgb, int h, int w, const char *text, d2s_stream_t stream);
 
+/* ---- occlusion-aware stereo rendering ----
+ * The reference's OpenGL viewer warps with a fragment shader that handles disocclusions (reference viewer.py:386-631:
+ * 3-tap depth smoothing, depth shaping, edge falloff, 2-tap disocclusion confidence :421-435, push-pull inpaint :437-506, border
+ * alpha, feathering, rounded corners); d2s_make_sbs_dibr evaluates that shader per output pixel of both eye views (left eye
+ * u_eye_offset = -ipd_uv/2, right +ipd_uv/2, u_depth_strength = 0.1 * depth_ratio; viewer.py:1334, 2680-2760) and packs them like
+ * the viewer's viewports: Full modes render each eye at frame size, Half-SBS / Half-TAB at half width / half height.
+ * The output is colour x alpha over black, scaled to 0..255 like d2s_make_sbs.  Parity: bit-exact against oracle/dibr_oracle.c
+ * (no OpenGL oracle exists: the reference never sets u_resolution, see that file's header). */
+typedef struct d2s_dibr_params {
+    d2s_image rgb;        /* source frame h x w, values 0..255 (u8 / f16 / f32); sampled as the normalised texture value / 255 */
+    d2s_image out;        /* packed frame, out_h x out_w (d2s_dibr_out_shape), f32 / f16 / u8 */
+    const void *depth;    /* [h, w] contiguous, F32 or F16: the texture the viewer uploads (predict_depth's map) */
+    int32_t depth_dtype;
+    int32_t h, w;
+    int32_t display_mode; /* enum d2s_display_mode */
+    double ipd_uv, depth_ratio, convergence, roll;   /* viewer.py:1326-1340; roll in radians (u_roll, 0 in the reference) */
+    float resolution_x, resolution_y;  /* u_resolution; <= 0: the eye view's size ("viewport resolution", viewer.py:395) */
+    int32_t search_radius;             /* 12   (u_search_radius, viewer.py:402) */
+    float depth_tolerance;             /* 0.012 (u_depth_tolerance) */
+    float blur_radius;                 /* 2.5  (u_blur_radius) */
+    int32_t feather_enabled;           /* 0    (viewer.py:1326 feather_enabled=False) */
+    float feather_width;
+    float corner_radius;               /* 0 */
+} d2s_dibr_params;
+int d2s_dibr_out_shape(int h, int w, int display_mode, int *view_h, int *view_w, int *out_h, int *out_w);
+int d2s_make_sbs_dibr(const d2s_dibr_params *p, d2s_stream_t stream);
+
 /* ---- whole-frame pipeline: the caller side of the hot path ----
  * Replaces the per-frame sequence main.py drives (reference main.py:232-262 process -> predict_depth, :1336-1341 make_sbs ->
  * streamer.set_frame) with ONE call per frame.  A pipe owns `slots` frame slots; each slot has a CUDA stream, fixed device
