@@ -280,7 +280,10 @@ def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, ou
                              stage_ms=dict(zip(["process", "resize+network+postprocess", "upsample+warp"], np.median(st, 0).tolist())))
         pipe.close()
     for name, odt in out_dtypes:
-        pipe = StereoPipeline(depth_slots=slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, out_dtype=odt, streams=streams)
+        fmt = "nv12" if name.endswith("nv12") else "rgb"
+        if fmt == "nv12":
+            oshape = ((streams,) if streams > 1 else ()) + (h * 3 // 2, 2 * w)
+        pipe = StereoPipeline(depth_slots=slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, out_dtype=odt, streams=streams, out_format=fmt)
 
         def run_host(idx, p=pipe):
             r = None
@@ -291,7 +294,7 @@ def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, ou
         assert tuple(r.shape) == oshape and r.dtype == {torch.float32: np.float32, torch.uint8: np.uint8}[odt]
         t = B.timed(run_host, steps)
         es = 4 if odt == torch.float32 else 1
-        h2d, d2h = fpp * h * w * 4, fpp * h * 2 * w * 3 * es
+        h2d, d2h = fpp * h * w * 4, (fpp * h * 2 * w * 3 * es if fmt == "rgb" else fpp * h * 2 * w * 3 // 2)
         fps = B.world * steps * fpp / (t["ms"] / 1e3)
         res[name] = dict(t, fps=fps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, pcie_gbs_per_gpu=(h2d + d2h) * fps / fpp / B.world / 1e9)
         pipe.close()
@@ -382,8 +385,8 @@ def main():
     serial_e2e(range(B.warmup))
     ms_serial_e2e = B.region(serial_e2e, n_serial)
 
-    legs = pipe_legs(B, depth, frames, host_frames, H, W, 1, args.slots, args.steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8)])
-    dv, e2e, e2e8 = legs["device"], legs["e2e"], legs["e2e_u8"]
+    legs = pipe_legs(B, depth, frames, host_frames, H, W, 1, args.slots, args.steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8)])
+    dv, e2e, e2e8, e2en = legs["device"], legs["e2e"], legs["e2e_u8"], legs["e2e_nv12"]
     host_bw = host_copy_bandwidth(B)
 
     # ---- rooflines (denominators: MEASURED_PEAKS.json, else the profiling guide's fallback) ----
@@ -439,6 +442,9 @@ def main():
             "e2e_u8": {"value": e2e8["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2e8["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e8["d2h_bytes_per_step"],
                        "pcie_gbs_per_gpu": e2e8["pcie_gbs_per_gpu"],
                        "note": "same loop, uint8 HWC frame packed by the warp kernel (4x fewer bytes over PCIe); what streamer.set_frame encodes (streamer.py:250-256)"},
+            "e2e_nv12": {"value": e2en["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2en["h2d_bytes_per_step"], "d2h_bytes_per_step": e2en["d2h_bytes_per_step"],
+                         "pcie_gbs_per_gpu": e2en["pcie_gbs_per_gpu"],
+                         "note": "same loop, NV12 frame (libjpeg colour conversion + 4:2:0 on the device, 1.5 B/px): 8x fewer bytes than float32"},
             "serial": {"note": "the drop-in calls one frame at a time on one stream (latency view); stage_ms = medians", "steps": n_serial,
                        "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
                        "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms},
@@ -472,11 +478,11 @@ def main():
     # compact copies inside the keys the driver's parser keeps (e2e / roofline / cpu_baseline), and a summary as the LAST key so the
     # tail of the line carries the 1080p and the 4K numbers side by side
     l4 = line.get("large4k")
-    line["e2e"]["legs"] = {"e2e_u8": e2e8["fps"], "serial_ms_per_frame_device": ms_serial / n_serial, "serial_ms_per_frame_e2e": ms_serial_e2e / n_serial}
+    line["e2e"]["legs"] = {"e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"], "serial_ms_per_frame_device": ms_serial / n_serial, "serial_ms_per_frame_e2e": ms_serial_e2e / n_serial}
     line["roofline"]["others"] = {"warp_1080p_hbm_frac": roofline_warp["frac"], "frame_graph_tensor_frac_in_flight": roofline_net["frac"],
                                   "frame_graph_tensor_frac_alone": roofline_net["isolated"]["frac"]}
     if l4:
-        line["e2e"]["legs"].update({"large4k_value": l4["value"], "large4k_e2e_fp32": l4["e2e"]["value"], "large4k_e2e_u8": l4["e2e_u8"]["value"]})
+        line["e2e"]["legs"].update({"large4k_value": l4["value"], "large4k_e2e_fp32": l4["e2e"]["value"], "large4k_e2e_u8": l4["e2e_u8"]["value"], "large4k_e2e_nv12": l4["e2e_nv12"]["value"]})
         line["roofline"]["others"].update({"warp_4k_hbm_frac": l4["roofline_warp"]["frac"], "gemm_m6224_tensor_frac": l4["roofline"]["frac"],
                                            "large4k_step_graph_tensor_frac": l4["roofline_net"]["frac"]})
         if "config5" in l4 and "value" in l4["config5"]:
@@ -488,8 +494,8 @@ def main():
         line["cpu_baseline"]["config1_one_thread"] = line["config1"]["cpu_1thread"]["value"]
         if "reference_cuda" in line:
             line["cpu_baseline"]["reference_torch_cuda_same_gpu"] = line["reference_cuda"]["value"]
-    line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"]},
-                       "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"]} if l4 else None),
+    line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"]},
+                       "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"], "e2e_nv12": l4["e2e_nv12"]["value"]} if l4 else None),
                        "reference_cuda_base1080": line.get("reference_cuda", {}).get("value"), "unit": "frames/s", "n_gpus": world}
     if rank == 0:
         print(json.dumps(line))
@@ -512,8 +518,8 @@ def large4k_block(B, args):
     host_frames = [f.cpu().pin_memory() for f in frames]
     steps = max(4, min(args.steps // 8, 16))    # a step = one frame of each of the 8 streams
     slots = 2
-    legs = pipe_legs(B, depth, frames, host_frames, h, w, S, slots, steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8)])
-    dv, e2e, e2e8 = legs["device"], legs["e2e"], legs["e2e_u8"]
+    legs = pipe_legs(B, depth, frames, host_frames, h, w, S, slots, steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8)])
+    dv, e2e, e2e8, e2en = legs["device"], legs["e2e"], legs["e2e_u8"], legs["e2e_nv12"]
     gflop = S * model_flops(cfg, 294, 518) / 1e9
     step_ms = dv["ms"] / steps
     net_tf = gflop / (step_ms * 1e-3) / 1e3
@@ -528,6 +534,8 @@ def large4k_block(B, args):
                    "limiter": "PCIe: 33 MB in + 199 MB out per 4K frame"},
            "e2e_u8": {"value": e2e8["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2e8["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e8["d2h_bytes_per_step"],
                       "pcie_gbs_per_gpu": e2e8["pcie_gbs_per_gpu"]},
+           "e2e_nv12": {"value": e2en["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2en["h2d_bytes_per_step"], "d2h_bytes_per_step": e2en["d2h_bytes_per_step"],
+                        "pcie_gbs_per_gpu": e2en["pcie_gbs_per_gpu"]},
            "target": {"north_star": ">= 60 frames/s end-to-end 4K depth + Full-SBS on 1 x B200", "met_fp32": e2e["fps"] / world >= 60, "met_u8": e2e8["fps"] / world >= 60},
            "roofline": {"kernel": "gemm_tc_persistent_kernel (tcgen05, cta_group::2), the 4 GEMMs of one ViT-L encoder layer at M = 6224", "bound": "tensor",
                         "achieved": fl / us / 1e6, "peak": B.peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / B.peaks["bf16_tflops"],

@@ -30,6 +30,7 @@ struct PipeSlot {
     void *ws_proc = nullptr, *ws_pre = nullptr, *ws_post = nullptr;
     void *d_depth = nullptr;         // [h,w] fp16: predict_depth's return value
     void *d_out = nullptr;           // packed stereo frame
+    void *d_nv12 = nullptr;          // cfg.out_nv12: the frame the caller receives ([oh * 3 / 2, ow] u8 per stream)
     void *h_in = nullptr, *h_out = nullptr;
     ShapePlan *plan = nullptr;
     cudaGraphExec_t gA = nullptr, gB = nullptr;
@@ -48,7 +49,7 @@ struct d2s_pipe {
     int h, w;          // size of process()'s output (== frame size unless target_height < frame_h)
     int Hm, Wm;        // model input
     int oh, ow;        // packed stereo frame
-    size_t frame_bytes, out_bytes, rgb_es, out_es;
+    size_t frame_bytes, out_bytes, res_bytes, rgb_es, out_es;   // out: the packed RGB frame, res: what the caller receives (per stream)
     size_t ws_proc_bytes, ws_pre_bytes, ws_post_bytes;
     void *ema_state = nullptr;               // [Hm,Wm] fp16, NaN = unset (d2s_post_params.ema_valid == 2)
     cudaEvent_t last_ema = nullptr;          // EMA event of the most recently submitted frame
@@ -57,6 +58,8 @@ struct d2s_pipe {
 };
 
 namespace d2s {
+
+int rgb_to_nv12_launch(const uint8_t *rgb, long long pitch, int h, int w, uint8_t *yp, uint8_t *uvp, cudaStream_t stream);   // nv12.cu
 
 static size_t dtype_size(int dt) { return dt == D2S_F32 ? 4 : (dt == D2S_U8 ? 1 : 2); }
 
@@ -114,9 +117,10 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     D2S_CHECK_CUDA(cudaMalloc(&s.ws_post, B * p->ws_post_bytes));     // (one per stream: its blur-x result waits there for the EMA step)
     D2S_CHECK_CUDA(cudaMalloc(&s.d_depth, (size_t)B * p->h * p->w * 2));
     D2S_CHECK_CUDA(cudaMalloc(&s.d_out, B * p->out_bytes));
+    if (c.out_nv12) D2S_CHECK_CUDA(cudaMalloc(&s.d_nv12, B * p->res_bytes));
     if (c.host_io) {
         D2S_CHECK_CUDA(cudaHostAlloc(&s.h_in, B * p->frame_bytes, cudaHostAllocDefault));
-        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_out, B * p->out_bytes, cudaHostAllocDefault));
+        D2S_CHECK_CUDA(cudaHostAlloc(&s.h_out, B * p->res_bytes, cudaHostAllocDefault));
     }
     TRY_RC(engine_plan(p->engine, B, p->Hm, p->Wm, D2S_F16, D2S_F16, s.stream, &s.plan));
 
@@ -134,6 +138,15 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
 
     const bool split = c.use_temporal_smooth != 0;
+    auto warp_and_pack = [&](int b) -> int {      // stereo warp (+ the NV12 stages of the output encoder)
+        d2s_warp_params wp; fill_warp(p, s, b, &wp);
+        int r = d2s_make_sbs(&wp, s.stream);
+        if (!r && c.out_nv12) {
+            uint8_t *nv = (uint8_t *)s.d_nv12 + (size_t)b * p->res_bytes;
+            r = rgb_to_nv12_launch((const uint8_t *)s.d_out + (size_t)b * p->out_bytes, (long long)p->ow * 3, p->oh, p->ow, nv, nv + (size_t)p->oh * p->ow, s.stream);
+        }
+        return r;
+    };
     // graph A
     long long k0 = g_launch_count.load();
     TRY_RC(capture_begin(s.stream));
@@ -146,7 +159,7 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     for (int b = 0; b < B && !rc; ++b) {
         d2s_post_params pp; fill_post(p, s, b, &pp);
         rc = postprocess_phases(&pp, split ? POST_PHASE_HEAD : POST_PHASE_ALL, s.stream);
-        if (!rc && !split) { d2s_warp_params wp; fill_warp(p, s, b, &wp); rc = d2s_make_sbs(&wp, s.stream); }
+        if (!rc && !split) rc = warp_and_pack(b);
     }
     TRY_RC(capture_end(s.stream, rc, &s.graphA, &s.gA));
     s.kernels_a = g_launch_count.load() - k0;
@@ -155,9 +168,8 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
         TRY_RC(capture_begin(s.stream));
         for (int b = 0; b < B && !rc; ++b) {
             d2s_post_params pp; fill_post(p, s, b, &pp);
-            d2s_warp_params wp; fill_warp(p, s, b, &wp);
             rc = postprocess_phases(&pp, POST_PHASE_UP, s.stream);
-            if (!rc) rc = d2s_make_sbs(&wp, s.stream);
+            if (!rc) rc = warp_and_pack(b);
         }
         TRY_RC(capture_end(s.stream, rc, &s.graphB, &s.gB));
         s.kernels_b = g_launch_count.load() - k0;
@@ -170,7 +182,7 @@ static void free_slot(PipeSlot &s) {
     if (s.gB) cudaGraphExecDestroy(s.gB);
     if (s.graphA) cudaGraphDestroy(s.graphA);
     if (s.graphB) cudaGraphDestroy(s.graphB);
-    for (void *q : {(void *)s.d_frame, s.d_rgb, s.ws_proc, s.ws_pre, s.ws_post, s.d_depth, s.d_out}) if (q) cudaFree(q);
+    for (void *q : {(void *)s.d_frame, s.d_rgb, s.ws_proc, s.ws_pre, s.ws_post, s.d_depth, s.d_out, s.d_nv12}) if (q) cudaFree(q);
     if (s.h_in) cudaFreeHost(s.h_in);
     if (s.h_out) cudaFreeHost(s.h_out);
     for (cudaEvent_t e : {s.done, s.ema_ev, s.in_ev, s.t[0], s.t[1], s.t[2], s.t[3]}) if (e) cudaEventDestroy(e);
@@ -207,6 +219,12 @@ extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2
     p->rgb_es = dtype_size(cfg->rgb_dtype); p->out_es = dtype_size(cfg->out_dtype);
     p->frame_bytes = (size_t)cfg->frame_h * cfg->frame_w * cfg->channels;
     p->out_bytes = (size_t)p->oh * p->ow * 3 * p->out_es;
+    p->res_bytes = cfg->out_nv12 ? (size_t)p->oh * p->ow * 3 / 2 : p->out_bytes;
+    if (cfg->out_nv12 && (cfg->out_dtype != D2S_U8 || p->oh % 2 || p->ow % 2)) {
+        rc = set_error(D2S_ERR_INVALID, "d2s_pipe_create: out_nv12 needs out_dtype U8 and an even-sized packed frame (%dx%d)", p->oh, p->ow);
+        delete p;
+        return rc;
+    }
     p->ws_proc_bytes = process_workspace_bytes(cfg->frame_h, cfg->frame_w, p->h, p->w);
     p->ws_pre_bytes = d2s_preprocess_workspace_bytes(p->h, p->w, p->Hm, p->Wm);
     p->ws_post_bytes = d2s_postprocess_workspace_bytes(p->Hm, p->Wm);
@@ -244,7 +262,7 @@ extern "C" int d2s_pipe_destroy(d2s_pipe_handle p) {
 extern "C" int d2s_pipe_geometry(d2s_pipe_handle p, int *h, int *w, int *model_h, int *model_w, int *out_h, int *out_w, size_t *frame_bytes, size_t *out_bytes) {
     D2S_REQUIRE(p != nullptr, "d2s_pipe_geometry: null pipe");
     if (h) *h = p->h; if (w) *w = p->w; if (model_h) *model_h = p->Hm; if (model_w) *model_w = p->Wm;
-    if (out_h) *out_h = p->oh; if (out_w) *out_w = p->ow; if (frame_bytes) *frame_bytes = p->frame_bytes; if (out_bytes) *out_bytes = p->out_bytes;
+    if (out_h) *out_h = p->oh; if (out_w) *out_w = p->ow; if (frame_bytes) *frame_bytes = p->frame_bytes; if (out_bytes) *out_bytes = p->res_bytes;
     return D2S_OK;
 }
 
@@ -252,7 +270,7 @@ extern "C" int d2s_pipe_slot_buffers(d2s_pipe_handle p, int slot, void **host_in
                                      d2s_stream_t *stream) {
     D2S_REQUIRE(p && slot >= 0 && slot < (int)p->slots.size(), "d2s_pipe_slot_buffers: bad slot");
     const PipeSlot &s = p->slots[slot];
-    if (host_in) *host_in = s.h_in; if (host_out) *host_out = s.h_out; if (dev_in) *dev_in = s.d_frame; if (dev_out) *dev_out = s.d_out;
+    if (host_in) *host_in = s.h_in; if (host_out) *host_out = s.h_out; if (dev_in) *dev_in = s.d_frame; if (dev_out) *dev_out = s.d_nv12 ? s.d_nv12 : s.d_out;
     if (dev_depth) *dev_depth = s.d_depth; if (stream) *stream = s.stream;
     return D2S_OK;
 }
@@ -294,7 +312,7 @@ extern "C" int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d
     }
     g_launch_count.fetch_add(kernels, std::memory_order_relaxed);
     if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[3], st));
-    if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, p->B * p->out_bytes, cudaMemcpyDeviceToHost, st));
+    if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_nv12 ? s.d_nv12 : s.d_out, p->B * p->res_bytes, cudaMemcpyDeviceToHost, st));
     D2S_CHECK_CUDA(cudaEventRecord(s.done, st));
     s.busy = true;
     return D2S_OK;

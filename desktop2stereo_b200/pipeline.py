@@ -53,6 +53,7 @@ class _Pipe:
         c.display_mode, c.fill_16_9 = DISPLAY_MODES[p["display_mode"]], int(bool(p["fill_16_9"]))
         c.out_dtype, c.slots, c.host_io = _TORCH2D2S[owner.out_dtype], owner.n_slots, int(host_io)
         c.streams = B = owner.streams
+        c.out_nv12 = int(owner.out_format == "nv12")
         self.handle = C.c_void_p()
         self.device, self.host_io, self.L = owner.device, host_io, L
         with torch.cuda.device(self.device):
@@ -69,11 +70,12 @@ class _Pipe:
             _lib.check(L.d2s_pipe_slot_buffers(self.handle, i, *[C.byref(x) for x in ptr]), "d2s_pipe_slot_buffers")
             hin, hout, _din, dout, ddep, st = [x.value for x in ptr]
             lead = (B,) if B > 1 else ()       # several streams: one frame of each per submit, stacked on a leading axis
+            oshape = (self.oh * 3 // 2, self.ow) if c.out_nv12 else (self.oh, self.ow, 3)
             if host_io:   # numpy views of the library's pinned buffers (no copy)
                 self.host_in.append(np.ctypeslib.as_array((C.c_uint8 * (B * fb.value)).from_address(hin)).reshape(lead + (h0, w0, ch)))
                 raw = np.ctypeslib.as_array((C.c_uint8 * (B * ob.value)).from_address(hout))
-                self.host_out.append(raw.view(_NP_OF[odt]).reshape(lead + (self.oh, self.ow, 3)))
-            self.dev_out.append(_device_view(dout, lead + (self.oh, self.ow, 3), odt, self.device))
+                self.host_out.append(raw.view(_NP_OF[odt]).reshape(lead + oshape))
+            self.dev_out.append(_device_view(dout, lead + oshape, odt, self.device))
             self.dev_depth.append(_device_view(ddep, lead + (self.h, self.w), torch.float16, self.device))
             self.streams.append(st)
 
@@ -99,11 +101,14 @@ def _device_view(ptr, shape, dtype, device):
 
 class StereoPipeline:
     def __init__(self, depth_slots: int = 3, display_mode="Full-SBS", ipd_uv=0.064, depth_ratio=2.0, convergence=0.0,
-                 fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None, streams=1):
+                 fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None, streams=1,
+                 out_format="rgb"):
         """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and the post-process settings live there).
         A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224).
         streams > 1: that many concurrent video streams share the pipeline; every submit takes one frame of each, stacked as
-        [streams, h, w, ch] (the network runs them as one batch; each stream has its own DepthStabilizer state)."""
+        [streams, h, w, ch] (the network runs them as one batch; each stream has its own DepthStabilizer state).
+        out_format="nv12" (with out_dtype=torch.uint8): results are NV12 frames [oh * 3 // 2, ow] u8 — the colour-conversion and
+        4:2:0 stages of the JPEG encoder the reference runs on the host (streamer.py:250-256), done on the device: 1.5 B/px."""
         d2s_depth._need_init()
         engine = d2s_depth.model_wraper.model
         if getattr(engine.cfg, "temporal", 0) and depth_slots != 1:
@@ -113,6 +118,9 @@ class StereoPipeline:
             raise ValueError(f"display_mode {display_mode!r}")
         self.device = d2s_depth.model_wraper.device if device is None else torch.device(device)
         self.n_slots, self.streams = depth_slots, int(streams)
+        if out_format not in ("rgb", "nv12") or (out_format == "nv12" and out_dtype != torch.uint8):
+            raise ValueError("out_format is 'rgb' or 'nv12' (nv12 needs out_dtype=torch.uint8)")
+        self.out_format = out_format
         self.params = dict(ipd_uv=ipd_uv, depth_ratio=depth_ratio, convergence=convergence, fill_16_9=fill_16_9,
                            display_mode=display_mode)
         self.use_temporal_smooth, self.out_dtype, self.target_height = use_temporal_smooth, out_dtype, target_height

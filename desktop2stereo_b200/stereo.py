@@ -99,6 +99,20 @@ def make_sbs_core(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ra
     return (out, il, ir) if return_indices else out
 
 
+def rgb_to_nv12(rgb_hwc: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Packed u8 HWC frame [h,w,3] -> NV12 [h*3//2, w] u8 (libjpeg's RGB->YCbCr + 4:2:0 stages, what cv2.imencode does first on
+    the frame the reference streams, streamer.py:250-256).  h, w even."""
+    _require_cuda(rgb_hwc, "rgb")
+    if rgb_hwc.dtype != torch.uint8 or rgb_hwc.dim() != 3 or rgb_hwc.shape[2] != 3 or rgb_hwc.stride(2) != 1 or rgb_hwc.stride(1) != 3:
+        raise ValueError("rgb_to_nv12 expects a uint8 [h,w,3] tensor with packed pixels")
+    h, w, _ = rgb_hwc.shape
+    if out is None:
+        out = torch.empty((h * 3 // 2, w), dtype=torch.uint8, device=rgb_hwc.device)
+    with torch.cuda.device(rgb_hwc.device):
+        _lib.check(_lib.lib().d2s_rgb_to_nv12(rgb_hwc.data_ptr(), rgb_hwc.stride(0), h, w, out.data_ptr(), _stream_ptr(rgb_hwc.device)), "d2s_rgb_to_nv12")
+    return out
+
+
 def make_sbs_dibr(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ratio=1.0, convergence=0.0, display_mode="Half-SBS", *,
                   roll=0.0, resolution=None, search_radius=12, depth_tolerance=0.012, blur_radius=2.5, feather_enabled=False,
                   feather_width=0.0, corner_radius=0.0, rgb_layout="CHW", out: torch.Tensor | None = None, out_dtype=torch.float32,

@@ -176,6 +176,12 @@ int d2s_postprocess(const d2s_post_params *p, d2s_stream_t stream);
 /* overlay_fps: blends the "FPS: xx.x" glyph mask into an RGB image in place. */
 int d2s_overlay_fps(const d2s_image *rgb, int h, int w, const char *text, d2s_stream_t stream);
 
+/* ---- device-side output encode, first stages ----
+ * Packed u8 HWC frame -> NV12 [h rows of Y | h/2 rows of interleaved CbCr], the colour conversion + 4:2:0 downsample of the JPEG
+ * encoder the reference runs on the host (cv2.imencode in streamer.py:250-256; libjpeg jccolor.c / jcsample.c arithmetic), 1.5 B/px:
+ * the layout NVENC / nvJPEG take.  h, w even.  row_pitch_bytes <= 0: tightly packed (3 * w). */
+int d2s_rgb_to_nv12(const uint8_t *rgb_hwc, int64_t row_pitch_bytes, int h, int w, uint8_t *nv12, d2s_stream_t stream);
+
 /* ---- occlusion-aware stereo rendering ----
  * The reference's OpenGL viewer warps with a fragment shader that handles disocclusions (reference viewer.py:386-631:
  * 3-tap depth smoothing, depth shaping, edge falloff, 2-tap disocclusion confidence :421-435, push-pull inpaint :437-506, border
@@ -227,12 +233,13 @@ typedef struct d2s_pipe_config {
     double ipd_uv, depth_ratio, convergence;   /* make_sbs (depth.py:2186) */
     int32_t display_mode, fill_16_9;
     int32_t out_dtype;            /* packed frame [oh, ow, 3] HWC: D2S_F32 = what make_sbs returns (depth.py:2231), D2S_U8, D2S_F16 */
+    int32_t out_nv12;             /* 1 (needs out_dtype U8, even oh / ow): the result is the NV12 frame [oh * 3 / 2, ow] u8 (d2s_rgb_to_nv12) */
     int32_t slots;                /* frames in flight (1..64); > 1 builds throughput-policy plans */
     int32_t host_io;              /* 1: frames come from and results go to pinned HOST memory (H2D / D2H copies on the slot's stream) */
     int32_t streams;              /* concurrent video streams sharing the pipe (0/1: one).  One submit takes ONE frame of EVERY stream:
                                      `frame` is [streams][frame_h, frame_w, channels], the result [streams][oh, ow, 3]; the network runs
                                      them as one batch (BASELINE configs 3/5: 8 x 4K), each stream keeps its own DepthStabilizer state */
-    int32_t reserved[2];
+    int32_t reserved[1];
 } d2s_pipe_config;
 int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2s_pipe_handle *out);
 int d2s_pipe_destroy(d2s_pipe_handle p);
