@@ -297,9 +297,12 @@ static int build_plan(d2s_engine *e, ShapePlan *sp) {
     const int heads = c.heads, mlp = c.mlp_hidden;
     // attention: the tcgen05 kernel (attention_tc.cu; V^T comes from the qkv GEMM's epilogue) when there are enough 128-query
     // tiles to fill the GPU (71 vs 101 us per layer at B = 8 x 16 heads), else the mma.sync flash kernel (equal at B = 1, and
-    // its 64-query tiles spread over more SMs).  D2S_ATTN=tcgen05 | mma forces one.
+    // its 64-query tiles spread over more SMs).  Throughput-policy plans (several frames in flight) always take the tcgen05 kernel:
+    // per-SM efficiency, not the latency of one launch, is what counts there (measured: 1796 -> 1866 frames/s at 8 frames in flight,
+    // base1080).  D2S_ATTN=tcgen05 | mma forces one.
     const char *attn_env = getenv("D2S_ATTN");
-    const bool attn_tc = attn_env && attn_env[0] ? attn_env[0] == 't' : (long long)B * heads * ceil_div(N, 128) >= 2 * kNumSMs;
+    const bool attn_tc = attn_env && attn_env[0] ? attn_env[0] == 't'
+                                                 : (sp->policy == D2S_POLICY_THROUGHPUT || (long long)B * heads * ceil_div(N, 128) >= 2 * kNumSMs);
     AttnTcPlan attn{};
     if (attn_tc) {
         __half *vt16;
