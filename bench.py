@@ -400,7 +400,7 @@ def main():
     net_tflops_iso = gflop / (serial_stage_ms["predict_depth"] * 1e-3) / 1e3
     net_tflops = gflop * args.steps / (dv["ms"] * 1e-3) / 1e3
     roofline_warp = {"kernel": "warp_sbs kernel (1080p)", "bound": "hbm", "achieved": warp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": traffic.get("warp_1080p"), "peak_source": src, "bytes_per_launch": warp_bytes,
+                     "frac": warp_gbs / peaks["hbm_gbs"], "traffic": (traffic.get("warp_1080p") or {}).get("bytes"), "traffic_detail": traffic.get("warp_1080p"), "peak_source": src, "bytes_per_launch": warp_bytes,
                      "duration_ms": serial_stage_ms["warp"], "timed": "alone on the GPU (serial leg), CUDA events on its stream, median of %d" % n_serial,
                      "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS"}
     roofline_net = {"kernel": "whole frame graph (resize + ViT-B + DPT on gemm_tc_kernel/tcgen05 + postprocess + warp), all kernels",
@@ -418,7 +418,7 @@ def main():
     us = sum(r["duration_us"] for r in own)
     roofline = {"kernel": "gemm_tc_kernel (tcgen05), the 4 GEMMs of one ViT-B encoder layer at M = 778 (qkv, proj, fc1+GELU, fc2)", "bound": "tensor",
                 "achieved": fl / us / 1e6, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / peaks["bf16_tflops"],
-                "traffic": traffic.get("gemm_m778"), "peak_source": src + " (burst: kernel timed alone)", "flops_per_launch": fl / len(own),
+                "traffic": (traffic.get("gemm_m778") or {}).get("bytes"), "traffic_detail": traffic.get("gemm_m778"), "peak_source": src + " (burst: kernel timed alone)", "flops_per_launch": fl / len(own),
                 "duration_us_per_launch": us / len(own), "launches": len(own),
                 "timed": "live: graph of 20 back-to-back launches per shape, CUDA events on their stream, L2-warm",
                 "note": "batch-1 shapes fill 42-126 of 148 SMs for ~10 us: latency-bound; the same kernel at batch 8 is in large4k.roofline"}
@@ -460,6 +460,7 @@ def main():
     # ================= the 4K half of the metric: configs[2] per GPU, configs[4] across GPUs =================
     if not args.no_large4k:
         line["large4k"] = large4k_block(B, args)
+        line["vda1080"] = vda1080_block(B, args)
     # ================= reference arms measured in the same run (rank 0, N = 1) =================
     if rank == 0 and world == 1 and not args.no_reference_cuda:
         rfps, rdt = cuda_reference_fps(30, 5, dev)
@@ -494,8 +495,11 @@ def main():
         line["cpu_baseline"]["config1_one_thread"] = line["config1"]["cpu_1thread"]["value"]
         if "reference_cuda" in line:
             line["cpu_baseline"]["reference_torch_cuda_same_gpu"] = line["reference_cuda"]["value"]
+    if "vda1080" in line:
+        line["e2e"]["legs"].update({"vda1080_value": line["vda1080"]["value"], "vda1080_e2e_fp32": line["vda1080"]["e2e"]})
     line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"]},
                        "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"], "e2e_nv12": l4["e2e_nv12"]["value"]} if l4 else None),
+                       "vda1080": ({"value": line["vda1080"]["value"], "e2e_fp32": line["vda1080"]["e2e"]} if "vda1080" in line else None),
                        "reference_cuda_base1080": line.get("reference_cuda", {}).get("value"), "unit": "frames/s", "n_gpus": world}
     if rank == 0:
         print(json.dumps(line))
@@ -539,7 +543,7 @@ def large4k_block(B, args):
            "target": {"north_star": ">= 60 frames/s end-to-end 4K depth + Full-SBS on 1 x B200", "met_fp32": e2e["fps"] / world >= 60, "met_u8": e2e8["fps"] / world >= 60},
            "roofline": {"kernel": "gemm_tc_persistent_kernel (tcgen05, cta_group::2), the 4 GEMMs of one ViT-L encoder layer at M = 6224", "bound": "tensor",
                         "achieved": fl / us / 1e6, "peak": B.peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / B.peaks["bf16_tflops"],
-                        "traffic": traffic.get("gemm_m6224"), "peak_source": B.peak_src + " (burst)", "per_shape": gem,
+                        "traffic": (traffic.get("gemm_m6224") or {}).get("bytes"), "traffic_detail": traffic.get("gemm_m6224"), "peak_source": B.peak_src + " (burst)", "per_shape": gem,
                         "timed": "live: graph of 20 back-to-back launches per shape, CUDA events on their stream"},
            "roofline_net": {"kernel": "whole step graph (8 x resize + ViT-L + DPT batch 8 + 8 x postprocess + 8 x warp)", "bound": "tensor",
                             "achieved": net_tf, "peak": B.peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": net_tf / B.peaks["bf16_tflops_sustained"],
@@ -565,6 +569,61 @@ def large4k_block(B, args):
         cfps, cdt = cpu_reference_fps(2, 1, threads, variant, h, w)
         out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                "sample": f"2 4K frames of DA-V2-Large after 1 warm-up ({cdt:.1f} s), one frame at a time"}
+    depth.model_wraper = None
+    engine.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def vda1080_block(B, args, videos=4, encoder="vits"):
+    """configs[3]: streaming Video-Depth-Anything, 1080p, 32-frame temporal window.  Frames of one video are sequential (the K/V rings
+    of the four temporal modules), so the unit of parallelism is the VIDEO: `videos` independent videos per GPU, each on its own
+    one-slot StereoPipeline (own CUDA stream, own window); across GPUs "replicas only" (video v -> rank v mod G, no collective).
+    A step = one frame of every video."""
+    import numpy as np
+    torch, dev, world = B.torch, B.dev, B.world
+    from desktop2stereo_b200 import depth
+    from desktop2stereo_b200.engine import B200Engine
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    from desktop2stereo_b200.synth import make_vda_state_dict
+    h, w = 1080, 1920
+    engine = B200Engine.from_vda_state_dict(make_vda_state_dict(encoder, SEED), encoder, dev, out_dtype=torch.float16)
+    depth.init(engine=engine, device=dev)
+    g = torch.Generator(device=dev).manual_seed(SEED + 200 + B.rank)
+    RING = 24
+    frames = [torch.randint(0, 256, (h, w, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(RING)]
+    host_frames = [f.cpu().pin_memory() for f in frames[:4]]
+    out = {"workload": WORKLOADS["vda1080"][4] + f" ({encoder}, model input 294x518), {videos} videos per GPU", "unit": "frames/s", "videos_per_gpu": videos}
+    steps = max(8, min(args.steps, 40))
+    for name, host in (("value", False), ("e2e", True)):
+        pipes = [StereoPipeline(depth_slots=1, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO) for _ in range(videos)]
+        src = host_frames if host else frames
+
+        def run(idx):
+            for i in idx:
+                for v, p in enumerate(pipes):
+                    if p.pending:
+                        p.result(host=host)
+                    f = src[(i * videos + v) % len(src)]
+                    p.submit_pinned(f) if host else p.submit_device(f)
+            for p in pipes:
+                while p.pending:
+                    p.result(host=host)
+        run(range(34))                      # past the 32-frame window: steady state
+        t = B.timed(run, steps)
+        out[name] = world * videos * steps / (t["ms"] / 1e3)
+        out[name + "_repeats"] = t["repeats"]
+        if not host:                        # one video alone: latency per frame
+            one = pipes[0]
+
+            def single(idx):
+                for i in idx:
+                    one.submit_device(frames[i % RING]); one.result(host=False)
+            ms = B.region(single, 20)
+            out["single_video_ms_per_frame"] = ms / 20
+        for p in pipes:
+            p.close()
+    out["steps"] = steps
     depth.model_wraper = None
     engine.close()
     torch.cuda.empty_cache()
@@ -597,7 +656,7 @@ def warp_roofline_4k(B, traffic):
     nbytes = h * w * (6 + 2 + 24)
     gbs = nbytes / (ms * 1e-3) / 1e9
     return {"kernel": "warp_sbs kernel (4K)", "bound": "hbm", "achieved": gbs, "peak": B.peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": gbs / B.peaks["hbm_gbs"], "traffic": traffic.get("warp_4k"), "bytes_per_launch": nbytes, "duration_ms": ms,
+            "unit": "GB/s", "frac": gbs / B.peaks["hbm_gbs"], "traffic": (traffic.get("warp_4k") or {}).get("bytes"), "traffic_detail": traffic.get("warp_4k"), "bytes_per_launch": nbytes, "duration_ms": ms,
             "timed": f"live: {2 * n} launches over {n} distinct 4K frame sets ({n * nbytes / 1e6:.0f} MB > L2) in a CUDA graph, events on its stream",
             "io": "rgb fp16 CHW + depth fp16 -> fp32 HWC Full-SBS", "peak_source": B.peak_src}
 
