@@ -449,6 +449,7 @@ def main():
                        "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
                        "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms},
             "stage_ms_in_flight": dv["stage_ms"],
+            "kernels_n2_n3": extra_kernel_legs(B),
         },
         "roofline": roofline, "roofline_warp": roofline_warp, "roofline_net": roofline_net, "roofline_gemm": gemms,
     }
@@ -688,6 +689,31 @@ def config1_block(B, threads):
             "cpu_1thread": {"value": c1, "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"2 frames ({d1:.1f} s)"},
             "cpu_all_cores": {"value": ca, "unit": "frames/s", "cores": threads, "kind": "port", "sample": f"4 frames ({da:.1f} s)"},
             "b200_serial_e2e": {"value": 50 / (ms / 1e3), "unit": "frames/s", "note": "process -> predict_depth -> make_sbs, host frame in, float32 host frame out, one at a time"}}
+
+
+def extra_kernel_legs(B):
+    """the widened rows' kernels alone, CUDA events around 10 launches at 1080p: the occlusion-aware DIBR renderer
+    on an edge-rich depth map (u8 frame + fp32 depth -> fp32 Full-SBS, 3 + 4 + 24 B/px) and the NV12 packer (3 B/px in, 1.5 B/px out)"""
+    torch, dev = B.torch, B.dev
+    from desktop2stereo_b200.stereo import make_sbs_dibr, rgb_to_nv12
+    h, w = 1080, 1920
+    g = torch.Generator(device=dev).manual_seed(3)
+    rgb = torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8, device=dev)
+    yy, xx = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+    dep = (0.2 + 0.6 * ((xx // 97 + yy // 53) % 2)).float()
+    out = torch.empty((h, 2 * w, 3), device=dev)
+    frame8 = torch.randint(0, 256, (h, 2 * w, 3), generator=g, dtype=torch.uint8, device=dev)
+    nv = torch.empty((h * 3 // 2, 2 * w), dtype=torch.uint8, device=dev)
+    res = {}
+    for name, fn, nbytes in (("dibr_1080p", lambda: make_sbs_dibr(rgb, dep, depth_ratio=2.0, display_mode="Full-SBS", out=out, out_layout="HWC"), h * w * (3 + 4 + 24)),
+                             ("nv12_1080p_full_sbs", lambda: rgb_to_nv12(frame8, out=nv), h * 2 * w * 4.5)):
+        for _ in range(3):
+            fn()
+        ms = B.region(lambda idx: [fn() for _ in idx], 10) / 10
+        res[name] = {"duration_us": ms * 1e3, "bytes_per_launch": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "peak_gbs": B.peaks["hbm_gbs"],
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / B.peaks["hbm_gbs"], "bound": "hbm"}
+    res["dibr_1080p"]["note"] = "gather-heavy (5 bilinear depth fetches + 1 colour fetch per pixel and eye, sweeps at depth edges): L2/latency-bound, not tuned"
+    return res
 
 
 def load_traffic():

@@ -10,7 +10,8 @@
 // reference sets neither), evaluated with exact fp32 weights.
 //
 // One thread = one output pixel of one eye; HBM/L2-gather bound, no tensor cores.  Strict fp32 in the shader's operation order,
-// compiled with -fmad=false, so the result is bit-identical to oracle/dibr_oracle.c (tests/test_dibr_gpu.py).  exp() weights and
+// compiled with -fmad=false, so the result is bit-identical to oracle/dibr_oracle.c (tests/test_dibr_gpu.py).  Texel coordinates
+// inside the image skip the GL_REPEAT wrap (fmodf) — same result, ~3x fewer instructions per fetch.  exp() weights and
 // cos/sin(roll) arrive as fp32 values computed on the host in double.  u_resolution is a parameter: the reference never sets it
 // (see the oracle's header), the default used by the host wrapper is the eye view's size, as the shader's comment says.
 #include "common.cuh"
@@ -29,11 +30,14 @@ struct DibrK {
     int feather; float feather_width, corner_radius;
 };
 
-__device__ __forceinline__ int wrap_texel(float f, int n) {   // GL_REPEAT
+__device__ __noinline__ int wrap_texel_slow(float f, int n) {   // GL_REPEAT for a texel coordinate outside [0, n)
     float r = fmodf(f, (float)n);
     if (r < 0.f) r = __fadd_rn(r, (float)n);
     int i = (int)r;
     return i >= n ? n - 1 : i;
+}
+__device__ __forceinline__ int wrap_texel(float f, int n) {     // f is integral (a floorf result): inside the image nothing wraps
+    return (f >= 0.f && f < (float)n) ? (int)f : wrap_texel_slow(f, n);
 }
 
 struct Taps { int x0, x1, y0, y1; float fx, fy; };
@@ -54,12 +58,13 @@ __device__ __forceinline__ float bilerp(float t00, float t10, float t01, float t
 }
 
 template <typename DT>
-__device__ __forceinline__ float tex_depth(const DibrK &k, float u, float v) {
-    const Taps t = make_taps(u, v, k.w, k.h);
+__device__ __forceinline__ float tex_depth_t(const DibrK &k, const Taps &t) {
     const DT *d = (const DT *)k.depth;
     const DT *r0 = d + (size_t)t.y0 * k.w, *r1 = d + (size_t)t.y1 * k.w;
     return bilerp(to_f32<DT>(__ldg(r0 + t.x0)), to_f32<DT>(__ldg(r0 + t.x1)), to_f32<DT>(__ldg(r1 + t.x0)), to_f32<DT>(__ldg(r1 + t.x1)), t.fx, t.fy);
 }
+template <typename DT>
+__device__ __forceinline__ float tex_depth(const DibrK &k, float u, float v) { return tex_depth_t<DT>(k, make_taps(u, v, k.w, k.h)); }
 
 // colour texel as the normalised texture holds it: value / 255 (the reference uploads u8 RGB, viewer.py:2385)
 template <typename RT>
@@ -67,14 +72,15 @@ __device__ __forceinline__ float texel(const DibrK &k, int c, int y, int x) {
     return __fdiv_rn(to_f32<RT>(__ldg((const RT *)k.rgb + c * k.rsc + (long long)y * k.rsy + (long long)x * k.rsx)), 255.f);
 }
 template <typename RT>
-__device__ __forceinline__ float3 tex_color(const DibrK &k, float u, float v) {
-    const Taps t = make_taps(u, v, k.w, k.h);
+__device__ __forceinline__ float3 tex_color_t(const DibrK &k, const Taps &t) {
     float o[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
         o[c] = bilerp(texel<RT>(k, c, t.y0, t.x0), texel<RT>(k, c, t.y0, t.x1), texel<RT>(k, c, t.y1, t.x0), texel<RT>(k, c, t.y1, t.x1), t.fx, t.fy);
     return make_float3(o[0], o[1], o[2]);
 }
+template <typename RT>
+__device__ __forceinline__ float3 tex_color(const DibrK &k, float u, float v) { return tex_color_t<RT>(k, make_taps(u, v, k.w, k.h)); }
 
 __device__ __forceinline__ float sstep(float e0, float e1, float x) {
     const float t = fminf(fmaxf(__fdiv_rn(__fsub_rn(x, e0), __fsub_rn(e1, e0)), 0.f), 1.f);
@@ -89,9 +95,10 @@ __device__ __noinline__ float3 push_pull(const DibrK &k, float ux, float uy, flo
     for (int i = 1; i <= k.search; ++i) {            // phase 1: sweep towards the side the background is revealed from
         const float qx = __fadd_rn(ux, __fmul_rn(swx, (float)i)), qy = __fadd_rn(uy, __fmul_rn(swy, (float)i));
         if (qx < 0.f || qy < 0.f || qx > 1.f || qy > 1.f) continue;
-        const float sdi = __fsub_rn(1.f, tex_depth<DT>(k, qx, qy));
+        const Taps tq = make_taps(qx, qy, k.w, k.h);       // depth and colour are fetched at the same coordinate
+        const float sdi = __fsub_rn(1.f, tex_depth_t<DT>(k, tq));
         if (sdi > thr) {
-            const float3 sc = tex_color<RT>(k, qx, qy);
+            const float3 sc = tex_color_t<RT>(k, tq);
             const float dw = __fadd_rn(1.f, __fmul_rn(__fsub_rn(sdi, center), 10.f));
             const float wgt = __fmul_rn(k.w1[i], dw);
             bx = __fadd_rn(bx, __fmul_rn(sc.x, wgt)); by = __fadd_rn(by, __fmul_rn(sc.y, wgt)); bz = __fadd_rn(bz, __fmul_rn(sc.z, wgt));
@@ -103,9 +110,10 @@ __device__ __noinline__ float3 push_pull(const DibrK &k, float ux, float uy, flo
         for (int i = 1; i <= k.search; ++i) {
             const float qx = __fsub_rn(ux, __fmul_rn(swx, (float)i)), qy = __fsub_rn(uy, __fmul_rn(swy, (float)i));
             if (qx < 0.f || qy < 0.f || qx > 1.f || qy > 1.f) continue;
-            const float sdi = __fsub_rn(1.f, tex_depth<DT>(k, qx, qy));
+            const Taps tq = make_taps(qx, qy, k.w, k.h);
+            const float sdi = __fsub_rn(1.f, tex_depth_t<DT>(k, tq));
             if (sdi > thr) {
-                const float3 sc = tex_color<RT>(k, qx, qy);
+                const float3 sc = tex_color_t<RT>(k, tq);
                 const float wgt = k.w2[i];
                 bx = __fadd_rn(bx, __fmul_rn(sc.x, wgt)); by = __fadd_rn(by, __fmul_rn(sc.y, wgt)); bz = __fadd_rn(bz, __fmul_rn(sc.z, wgt));
                 bw = __fadd_rn(bw, wgt);
