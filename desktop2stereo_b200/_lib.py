@@ -58,7 +58,7 @@ class DibrParams(C.Structure):
                 ("display_mode", C.c_int32), ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
                 ("roll", C.c_double), ("resolution_x", C.c_float), ("resolution_y", C.c_float), ("search_radius", C.c_int32),
                 ("depth_tolerance", C.c_float), ("blur_radius", C.c_float), ("feather_enabled", C.c_int32),
-                ("feather_width", C.c_float), ("corner_radius", C.c_float)]
+                ("feather_width", C.c_float), ("corner_radius", C.c_float), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class PipeConfig(C.Structure):
@@ -94,6 +94,7 @@ SYMBOLS = {
     "d2s_postprocess": (C.c_int, [C.POINTER(PostParams), C.c_void_p]),
     "d2s_overlay_fps": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_char_p, C.c_void_p]),
     "d2s_rgb_to_nv12": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "d2s_dibr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "d2s_dibr_out_shape": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "d2s_make_sbs_dibr": (C.c_int, [C.POINTER(DibrParams), C.c_void_p]),
     "d2s_pipe_create": (C.c_int, [C.c_void_p, C.POINTER(PipeConfig), C.POINTER(C.c_void_p)]),

@@ -141,10 +141,10 @@ __device__ __noinline__ float3 push_pull(const DibrK &k, float ux, float uy, flo
     return tex_color<RT>(k, ux, uy);
 }
 
-template <typename RT, typename DT, typename OT>
-__global__ void __launch_bounds__(256) dibr_kernel(const __grid_constant__ DibrK k) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, e = blockIdx.z;
-    if (j >= k.vw) return;
+// One output pixel (view column j, view row i from the top, eye e).  DEFER: a pixel whose disocclusion confidence calls for the
+// inpaint sweep is not finished here — it returns true and the caller queues it for the dense second pass.
+template <typename RT, typename DT, typename OT, bool DEFER>
+__device__ __forceinline__ bool dibr_pixel(const DibrK &k, int j, int i, int e) {
     const float eye = e ? k.ipd_half : -k.ipd_half;
     const float uvx = __fdiv_rn(__fadd_rn((float)j, 0.5f), (float)k.vw);
     const float uvy = __fdiv_rn(__fadd_rn((float)(k.vh - 1 - i), 0.5f), (float)k.vh);     // gl_FragCoord.y counts from the bottom
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) dibr_kernel(const __grid_constant__ DibrK
         const float dl = tex_depth<DT>(k, __fsub_rn(fx, s2x), __fsub_rn(fy, s2y)), dr = tex_depth<DT>(k, __fadd_rn(fx, s2x), __fadd_rn(fy, s2y));
         conf = sstep(0.04f, 0.10f, fabsf(__fsub_rn(dl, dr)));
     }
+    if (DEFER && conf > 0.001f) return true;
     float3 col = tex_color<RT>(k, sx, sy);
     if (conf > 0.001f) {
         const float3 f = push_pull<RT, DT>(k, fx, fy, depth_inv, pdx, pdy, psx, psy, sweep_sign);
@@ -202,23 +203,66 @@ __global__ void __launch_bounds__(256) dibr_kernel(const __grid_constant__ DibrK
     const float v[3] = {col.x, col.y, col.z};
 #pragma unroll
     for (int c = 0; c < 3; ++c) o[c * k.osc] = from_f32<OT>(__fmul_rn(fminf(fmaxf(__fmul_rn(v[c], alpha), 0.f), 1.f), 255.f));
+    return false;
 }
 
-template <typename RT, typename DT>
-static int launch_dibr_out(const DibrK &k, dim3 grid, d2s_stream_t st) {
-    switch (k.out_dtype) {
-        case D2S_F32: D2S_LAUNCH((dibr_kernel<RT, DT, float>), grid, 256, 0, st, k); break;
-        case D2S_U8: D2S_LAUNCH((dibr_kernel<RT, DT, uint8_t>), grid, 256, 0, st, k); break;
-        case D2S_F16: D2S_LAUNCH((dibr_kernel<RT, DT, __half>), grid, 256, 0, st, k); break;
-        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs_dibr: out dtype %d", k.out_dtype);
+// single pass: every pixel finished by its own thread (no workspace)
+template <typename RT, typename DT, typename OT>
+__global__ void __launch_bounds__(256) dibr_kernel(const __grid_constant__ DibrK k) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k.vw) return;
+    dibr_pixel<RT, DT, OT, false>(k, j, blockIdx.y, blockIdx.z);
+}
+
+// Two passes (with a caller workspace).  The inpaint sweep runs up to 2 x search_radius (depth + colour) fetches for the few
+// per cent of pixels that sit on a depth edge; in the single-pass kernel every warp that contains ONE such pixel walks the whole sweep
+// with 31 idle lanes.  Pass A finishes the ordinary pixels and queues the others (one warp-aggregated atomic per warp); pass B
+// runs the queued pixels densely, one per thread, persistent blocks striding over the queue.  Same per-pixel function, so the
+// frame is bit-identical to the single-pass kernel's.
+template <typename RT, typename DT, typename OT>
+__global__ void __launch_bounds__(256) dibr_pass_a_kernel(const __grid_constant__ DibrK k, uint32_t *__restrict__ queue, uint32_t *__restrict__ count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, e = blockIdx.z;
+    const bool defer = j < k.vw && dibr_pixel<RT, DT, OT, true>(k, j, i, e);
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (defer) queue[base + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)e << 31) | ((uint32_t)i << 16) | (uint32_t)j;
     }
+}
+template <typename RT, typename DT, typename OT>
+__global__ void __launch_bounds__(128) dibr_pass_b_kernel(const __grid_constant__ DibrK k, const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
+    const uint32_t n = *count;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t v = queue[q];
+        dibr_pixel<RT, DT, OT, false>(k, (int)(v & 0xffffu), (int)((v >> 16) & 0x7fffu), (int)(v >> 31));
+    }
+}
+
+template <typename RT, typename DT, typename OT>
+static int launch_dibr_t(const DibrK &k, dim3 grid, uint32_t *ws, d2s_stream_t st) {
+    if (!ws) { D2S_LAUNCH((dibr_kernel<RT, DT, OT>), grid, 256, 0, st, k); return D2S_OK; }
+    D2S_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(uint32_t), (cudaStream_t)st));     // ws[0] = queue length, ws[4..] = queue
+    D2S_LAUNCH((dibr_pass_a_kernel<RT, DT, OT>), grid, 256, 0, st, k, ws + 4, ws);
+    D2S_LAUNCH((dibr_pass_b_kernel<RT, DT, OT>), 8 * kNumSMs, 128, 0, st, k, ws + 4, ws);
     return D2S_OK;
 }
+template <typename RT, typename DT>
+static int launch_dibr_out(const DibrK &k, dim3 grid, uint32_t *ws, d2s_stream_t st) {
+    switch (k.out_dtype) {
+        case D2S_F32: return launch_dibr_t<RT, DT, float>(k, grid, ws, st);
+        case D2S_U8: return launch_dibr_t<RT, DT, uint8_t>(k, grid, ws, st);
+        case D2S_F16: return launch_dibr_t<RT, DT, __half>(k, grid, ws, st);
+        default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs_dibr: out dtype %d", k.out_dtype);
+    }
+}
 template <typename RT>
-static int launch_dibr_depth(const DibrK &k, dim3 grid, d2s_stream_t st) {
+static int launch_dibr_depth(const DibrK &k, dim3 grid, uint32_t *ws, d2s_stream_t st) {
     switch (k.depth_dtype) {
-        case D2S_F32: return launch_dibr_out<RT, float>(k, grid, st);
-        case D2S_F16: return launch_dibr_out<RT, __half>(k, grid, st);
+        case D2S_F32: return launch_dibr_out<RT, float>(k, grid, ws, st);
+        case D2S_F16: return launch_dibr_out<RT, __half>(k, grid, ws, st);
         default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs_dibr: depth dtype %d", k.depth_dtype);
     }
 }
@@ -235,6 +279,12 @@ extern "C" int d2s_dibr_out_shape(int h, int w, int display_mode, int *view_h, i
     if (view_h) *view_h = vh; if (view_w) *view_w = vw;
     if (out_h) *out_h = tab ? 2 * vh : vh; if (out_w) *out_w = tab ? vw : 2 * vw;
     return D2S_OK;
+}
+
+extern "C" size_t d2s_dibr_workspace_bytes(int h, int w, int display_mode) {
+    int vh, vw, oh, ow;
+    if (d2s_dibr_out_shape(h, w, display_mode, &vh, &vw, &oh, &ow)) return 0;
+    return sizeof(uint32_t) * (4 + (size_t)2 * vh * vw);      // a counter + one queue slot per output pixel (worst case: every pixel deferred)
 }
 
 extern "C" int d2s_make_sbs_dibr(const d2s_dibr_params *p, d2s_stream_t stream) {
@@ -262,11 +312,17 @@ extern "C" int d2s_make_sbs_dibr(const d2s_dibr_params *p, d2s_stream_t stream) 
     for (int i = 0; i <= 32; ++i) { k.w1[i] = (float)exp(-(double)i * 0.15); k.w2[i] = (float)exp(-(double)i * 0.2); }
     k.feather = p->feather_enabled; k.feather_width = p->feather_width; k.corner_radius = p->corner_radius;
     dim3 grid(ceil_div(k.vw, 256), k.vh, 2);
-    D2S_REQUIRE(k.vh <= 65535, "d2s_make_sbs_dibr: view height %d", k.vh);
+    D2S_REQUIRE(k.vh <= 32767 && k.vw <= 65535, "d2s_make_sbs_dibr: eye view %dx%d too large", k.vh, k.vw);
+    uint32_t *ws = nullptr;
+    if (p->workspace) {
+        D2S_REQUIRE(p->workspace_bytes >= d2s_dibr_workspace_bytes(p->h, p->w, p->display_mode) && ((uintptr_t)p->workspace & 15) == 0,
+                    "d2s_make_sbs_dibr: workspace too small or misaligned (%zu bytes, need %zu)", p->workspace_bytes, d2s_dibr_workspace_bytes(p->h, p->w, p->display_mode));
+        ws = (uint32_t *)p->workspace;
+    }
     switch (p->rgb.dtype) {
-        case D2S_U8: rc = launch_dibr_depth<uint8_t>(k, grid, stream); break;
-        case D2S_F16: rc = launch_dibr_depth<__half>(k, grid, stream); break;
-        case D2S_F32: rc = launch_dibr_depth<float>(k, grid, stream); break;
+        case D2S_U8: rc = launch_dibr_depth<uint8_t>(k, grid, ws, stream); break;
+        case D2S_F16: rc = launch_dibr_depth<__half>(k, grid, ws, stream); break;
+        case D2S_F32: rc = launch_dibr_depth<float>(k, grid, ws, stream); break;
         default: return set_error(D2S_ERR_UNSUPPORTED, "d2s_make_sbs_dibr: rgb dtype %d", p->rgb.dtype);
     }
     if (rc) return rc;

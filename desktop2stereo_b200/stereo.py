@@ -116,7 +116,7 @@ def rgb_to_nv12(rgb_hwc: torch.Tensor, out: torch.Tensor | None = None) -> torch
 def make_sbs_dibr(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ratio=1.0, convergence=0.0, display_mode="Half-SBS", *,
                   roll=0.0, resolution=None, search_radius=12, depth_tolerance=0.012, blur_radius=2.5, feather_enabled=False,
                   feather_width=0.0, corner_radius=0.0, rgb_layout="CHW", out: torch.Tensor | None = None, out_dtype=torch.float32,
-                  out_layout="CHW"):
+                  out_layout="CHW", two_pass=True):
     """The reference viewer's occlusion-aware stereo rendering (viewer.py:386-631: disocclusion confidence + push-pull inpaint) as
     a tensor function: rgb [3,h,w] (0..255) + depth [h,w] -> packed frame [3,oh,ow] (or HWC), both eye views side by side / top-bottom
     as StereoWindow.render lays them out (viewer.py:2680-2760).  Defaults are the viewer's (ipd 0.064, depth_ratio 1.0, viewer.py:1326).
@@ -144,6 +144,10 @@ def make_sbs_dibr(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ra
     p.resolution_x, p.resolution_y = (resolution if resolution is not None else (0.0, 0.0))
     p.search_radius, p.depth_tolerance, p.blur_radius = int(search_radius), float(depth_tolerance), float(blur_radius)
     p.feather_enabled, p.feather_width, p.corner_radius = int(bool(feather_enabled)), float(feather_width), float(corner_radius)
+    if two_pass:      # scratch for the dense second pass over the pixels that need the inpaint sweep (per stream, like the other workspaces)
+        from .prepost import _workspace
+        ws = _workspace(rgb.device, L.d2s_dibr_workspace_bytes(h, w, DISPLAY_MODES[display_mode]), "dibr")
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     with torch.cuda.device(rgb.device):
         _lib.check(L.d2s_make_sbs_dibr(C.byref(p), _stream_ptr(rgb.device)), "d2s_make_sbs_dibr")
     return out

@@ -205,7 +205,11 @@ typedef struct d2s_dibr_params {
     int32_t feather_enabled;           /* 0    (viewer.py:1326 feather_enabled=False) */
     float feather_width;
     float corner_radius;               /* 0 */
+    void *workspace;                   /* optional device scratch (16-byte aligned, d2s_dibr_workspace_bytes): with it the inpaint sweeps of
+                                          the pixels on depth edges run in a dense second pass (same frame, ~3x faster); NULL: one pass */
+    size_t workspace_bytes;
 } d2s_dibr_params;
+size_t d2s_dibr_workspace_bytes(int h, int w, int display_mode);
 int d2s_dibr_out_shape(int h, int w, int display_mode, int *view_h, int *view_w, int *out_h, int *out_w);
 int d2s_make_sbs_dibr(const d2s_dibr_params *p, d2s_stream_t stream);
 

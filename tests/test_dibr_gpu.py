@@ -35,6 +35,18 @@ def test_dibr_bit_exact_vs_oracle(cuda_device, mode):
     assert (cl > 0.001).mean() > 0.005 and (cr > 0.001).mean() > 0.005
 
 
+def test_dibr_two_pass_equals_single_pass(cuda_device):
+    """the dense second pass over the queued edge pixels produces the same frame as the one-pass kernel, bit for bit"""
+    from desktop2stereo_b200.stereo import make_sbs_dibr
+    for (h, w, seed) in [(360, 640, 7), (135, 241, 8)]:
+        rgb, depth = _scene(seed, h, w)
+        r, d = torch.from_numpy(rgb).to(cuda_device), torch.from_numpy(depth).to(cuda_device)
+        for mode in MODES:
+            a = make_sbs_dibr(r, d, depth_ratio=4.0, display_mode=mode, rgb_layout="HWC", two_pass=True)
+            b = make_sbs_dibr(r, d, depth_ratio=4.0, display_mode=mode, rgb_layout="HWC", two_pass=False)
+            assert torch.equal(a, b), (h, w, mode)
+
+
 def test_dibr_feather_dtypes_layouts(cuda_device):
     from desktop2stereo_b200.stereo import make_sbs_dibr
     h, w = 72, 128
