@@ -37,6 +37,11 @@ struct PipeSlot {
     cudaGraph_t graphA = nullptr, graphB = nullptr;
     long long kernels_a = 0, kernels_b = 0;
     bool busy = false, traced = false;
+    // streams > 1: the per-stream resize / post-process / warp chains of one step are independent: they are captured as parallel
+    // branches of the graphs (fork / join through these), so e.g. the eight one-block percentile selections run side by side
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> join_ev;
+    cudaEvent_t fork_ev = nullptr;
 };
 
 }  // namespace d2s
@@ -60,6 +65,8 @@ struct d2s_pipe {
 namespace d2s {
 
 int rgb_to_nv12_launch(const uint8_t *rgb, long long pitch, int h, int w, uint8_t *yp, uint8_t *uvp, cudaStream_t stream);   // nv12.cu
+
+__global__ void pipe_join_kernel(int) {}      // a single kernel predecessor for whatever follows a join (programmatic launch edges need one)
 
 static size_t dtype_size(int dt) { return dt == D2S_F32 ? 4 : (dt == D2S_U8 ? 1 : 2); }
 
@@ -113,7 +120,15 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     D2S_CHECK_CUDA(cudaMalloc((void **)&s.d_frame, B * p->frame_bytes));
     D2S_CHECK_CUDA(cudaMalloc(&s.d_rgb, (size_t)B * 3 * p->h * p->w * p->rgb_es));
     if (p->ws_proc_bytes) D2S_CHECK_CUDA(cudaMalloc(&s.ws_proc, p->ws_proc_bytes));
-    D2S_CHECK_CUDA(cudaMalloc(&s.ws_pre, p->ws_pre_bytes));
+    D2S_CHECK_CUDA(cudaMalloc(&s.ws_pre, B * p->ws_pre_bytes));       // (one per stream: the resizes of one step run concurrently)
+    if (B > 1) {
+        s.aux.resize(B); s.join_ev.resize(B);
+        for (int b = 0; b < B; ++b) {
+            D2S_CHECK_CUDA(cudaStreamCreateWithFlags(&s.aux[b], cudaStreamNonBlocking));
+            D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.join_ev[b], cudaEventDisableTiming));
+        }
+        D2S_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming));
+    }
     D2S_CHECK_CUDA(cudaMalloc(&s.ws_post, B * p->ws_post_bytes));     // (one per stream: its blur-x result waits there for the EMA step)
     D2S_CHECK_CUDA(cudaMalloc(&s.d_depth, (size_t)B * p->h * p->w * 2));
     D2S_CHECK_CUDA(cudaMalloc(&s.d_out, B * p->out_bytes));
@@ -132,45 +147,63 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
         return v;
     };
     auto model_in = [&](int b) { return (void *)((__half *)s.plan->in_stage + (size_t)b * 3 * p->Hm * p->Wm); };
-    d2s_image src0 = rgb_view(0);
+    auto ws_pre_of = [&](int b) { return (void *)((char *)s.ws_pre + (size_t)b * p->ws_pre_bytes); };
     TRY_RC(process_phases(s.d_frame, c.frame_h, c.frame_w, c.channels, s.d_rgb, c.rgb_dtype, p->h, p->w, s.ws_proc, p->ws_proc_bytes, 1, s.stream));
-    TRY_RC(preprocess_phases(&src0, p->h, p->w, model_in(0), D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 1, s.stream));
+    for (int b = 0; b < B; ++b) {
+        d2s_image src = rgb_view(b);
+        TRY_RC(preprocess_phases(&src, p->h, p->w, model_in(b), D2S_F16, p->Hm, p->Wm, c.mean, c.std, ws_pre_of(b), p->ws_pre_bytes, 1, s.stream));
+    }
     D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
 
     const bool split = c.use_temporal_smooth != 0;
-    auto warp_and_pack = [&](int b) -> int {      // stereo warp (+ the NV12 stages of the output encoder)
+    auto warp_and_pack = [&](int b, cudaStream_t st) -> int {      // stereo warp (+ the NV12 stages of the output encoder)
         d2s_warp_params wp; fill_warp(p, s, b, &wp);
-        int r = d2s_make_sbs(&wp, s.stream);
+        int r = d2s_make_sbs(&wp, st);
         if (!r && c.out_nv12) {
             uint8_t *nv = (uint8_t *)s.d_nv12 + (size_t)b * p->res_bytes;
-            r = rgb_to_nv12_launch((const uint8_t *)s.d_out + (size_t)b * p->out_bytes, (long long)p->ow * 3, p->oh, p->ow, nv, nv + (size_t)p->oh * p->ow, s.stream);
+            r = rgb_to_nv12_launch((const uint8_t *)s.d_out + (size_t)b * p->out_bytes, (long long)p->ow * 3, p->oh, p->ow, nv, nv + (size_t)p->oh * p->ow, st);
         }
+        return r;
+    };
+    // run body(b, stream) for every stream of the step: in line for one stream, as parallel branches of the capture otherwise
+    auto for_each_stream = [&](auto body) -> int {
+        if (B == 1) return body(0, s.stream);
+        D2S_CHECK_CUDA(cudaEventRecord(s.fork_ev, s.stream));
+        int r = D2S_OK;
+        for (int b = 0; b < B; ++b) {
+            D2S_CHECK_CUDA(cudaStreamWaitEvent(s.aux[b], s.fork_ev, 0));
+            if (!r) r = body(b, s.aux[b]);
+            D2S_CHECK_CUDA(cudaEventRecord(s.join_ev[b], s.aux[b]));
+            D2S_CHECK_CUDA(cudaStreamWaitEvent(s.stream, s.join_ev[b], 0));
+        }
+        D2S_LAUNCH(pipe_join_kernel, 1, 1, 0, s.stream, 0);
         return r;
     };
     // graph A
     long long k0 = g_launch_count.load();
     TRY_RC(capture_begin(s.stream));
-    int rc = D2S_OK;
-    for (int b = 0; b < B && !rc; ++b) {
+    int rc = for_each_stream([&](int b, cudaStream_t st) {
         d2s_image src = rgb_view(b);
-        rc = preprocess_phases(&src, p->h, p->w, model_in(b), D2S_F16, p->Hm, p->Wm, c.mean, c.std, s.ws_pre, p->ws_pre_bytes, 2, s.stream);
-    }
+        return preprocess_phases(&src, p->h, p->w, model_in(b), D2S_F16, p->Hm, p->Wm, c.mean, c.std, ws_pre_of(b), p->ws_pre_bytes, 2, st);
+    });
     if (!rc) rc = engine_run_ops(s.plan, s.stream);
-    for (int b = 0; b < B && !rc; ++b) {
+    if (!rc) rc = for_each_stream([&](int b, cudaStream_t st) {
         d2s_post_params pp; fill_post(p, s, b, &pp);
-        rc = postprocess_phases(&pp, split ? POST_PHASE_HEAD : POST_PHASE_ALL, s.stream);
-        if (!rc && !split) rc = warp_and_pack(b);
-    }
+        int r = postprocess_phases(&pp, split ? POST_PHASE_HEAD : POST_PHASE_ALL, st);
+        if (!r && !split) r = warp_and_pack(b, st);
+        return r;
+    });
     TRY_RC(capture_end(s.stream, rc, &s.graphA, &s.gA));
     s.kernels_a = g_launch_count.load() - k0;
     if (split) {
         k0 = g_launch_count.load();
         TRY_RC(capture_begin(s.stream));
-        for (int b = 0; b < B && !rc; ++b) {
+        rc = for_each_stream([&](int b, cudaStream_t st) {
             d2s_post_params pp; fill_post(p, s, b, &pp);
-            rc = postprocess_phases(&pp, POST_PHASE_UP, s.stream);
-            if (!rc) rc = warp_and_pack(b);
-        }
+            int r = postprocess_phases(&pp, POST_PHASE_UP, st);
+            if (!r) r = warp_and_pack(b, st);
+            return r;
+        });
         TRY_RC(capture_end(s.stream, rc, &s.graphB, &s.gB));
         s.kernels_b = g_launch_count.load() - k0;
     }
@@ -185,7 +218,9 @@ static void free_slot(PipeSlot &s) {
     for (void *q : {(void *)s.d_frame, s.d_rgb, s.ws_proc, s.ws_pre, s.ws_post, s.d_depth, s.d_out, s.d_nv12}) if (q) cudaFree(q);
     if (s.h_in) cudaFreeHost(s.h_in);
     if (s.h_out) cudaFreeHost(s.h_out);
-    for (cudaEvent_t e : {s.done, s.ema_ev, s.in_ev, s.t[0], s.t[1], s.t[2], s.t[3]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.done, s.ema_ev, s.in_ev, s.fork_ev, s.t[0], s.t[1], s.t[2], s.t[3]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.join_ev) if (e) cudaEventDestroy(e);
+    for (cudaStream_t a : s.aux) if (a) cudaStreamDestroy(a);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
