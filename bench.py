@@ -302,15 +302,29 @@ def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, ou
 
 
 def host_copy_bandwidth(B, nbytes=256 << 20):
-    """measured D2H and H2D rates of this rank's pinned memory (all ranks copy at the same time): names the limiter of the fp32 e2e row"""
+    """measured D2H / H2D rates of this rank's pinned memory — each direction alone and both at once, every rank copying at the same
+    time (max over ranks of the elapsed time): names the limiter of the e2e rows.  `aggregate_both_gbs` = all ranks, both directions."""
     torch = B.torch
-    hbuf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    dbuf = torch.empty(nbytes, dtype=torch.uint8, device=B.dev)
+    hbuf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True); hbuf2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dbuf = torch.empty(nbytes, dtype=torch.uint8, device=B.dev); dbuf2 = torch.empty(nbytes, dtype=torch.uint8, device=B.dev)
+    s2 = torch.cuda.Stream(B.dev)
     out = {}
     for name, (dst, src) in {"d2h_gbs": (hbuf, dbuf), "h2d_gbs": (dbuf, hbuf)}.items():
         dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
         ms = B.region(lambda idx: [dst.copy_(src, non_blocking=True) for _ in idx], 8)
         out[name] = 8 * nbytes / (ms / 1e3) / 1e9
+
+    def both(idx):
+        for _ in idx:
+            hbuf.copy_(dbuf, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dbuf2.copy_(hbuf2, non_blocking=True)
+        torch.cuda.current_stream(B.dev).wait_stream(s2)
+    both(range(1)); torch.cuda.synchronize()
+    ms = B.region(both, 8)
+    out["both_directions_gbs_per_gpu"] = 2 * 8 * nbytes / (ms / 1e3) / 1e9
+    out["aggregate_both_gbs"] = out["both_directions_gbs_per_gpu"] * B.world
+    out["note"] = "pinned-memory copies of 256 MB, all ranks at once; the e2e rows move h2d_bytes_per_step + d2h_bytes_per_step per frame through this"
     return out
 
 
@@ -416,12 +430,19 @@ def main():
     own = [r for r in gemms if r["M"] == 778]
     fl = sum(2.0 * r["M"] * r["N"] * r["K"] for r in own)
     us = sum(r["duration_us"] for r in own)
+    inf = gemm_in_flight(dev, peaks, src, streams=args.slots)
+    # `roofline` = the kernel as the timed region runs it (`slots` frames in flight, throughput-policy tiles, sustained peak);
+    # `isolated` = one launch alone on the GPU against the burst peak (the latency view)
     roofline = {"kernel": "gemm_tc_kernel (tcgen05), the 4 GEMMs of one ViT-B encoder layer at M = 778 (qkv, proj, fc1+GELU, fc2)", "bound": "tensor",
-                "achieved": fl / us / 1e6, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / peaks["bf16_tflops"],
-                "traffic": (traffic.get("gemm_m778") or {}).get("bytes"), "traffic_detail": traffic.get("gemm_m778"), "peak_source": src + " (burst: kernel timed alone)", "flops_per_launch": fl / len(own),
-                "duration_us_per_launch": us / len(own), "launches": len(own),
-                "timed": "live: graph of 20 back-to-back launches per shape, CUDA events on their stream, L2-warm",
-                "note": "batch-1 shapes fill 42-126 of 148 SMs for ~10 us: latency-bound; the same kernel at batch 8 is in large4k.roofline"}
+                "achieved": inf["achieved"], "peak": inf["peak"], "unit": "TFLOP/s", "frac": inf["frac"],
+                "traffic": (traffic.get("gemm_m778") or {}).get("bytes"), "traffic_detail": traffic.get("gemm_m778"),
+                "peak_source": inf["peak_source"], "flops_per_launch": inf["flops_per_launch"], "duration_us_per_launch": inf["duration_us_per_launch"],
+                "launches": inf["launches"], "streams": inf["streams"], "timed": inf["timed"],
+                "isolated": {"achieved": fl / us / 1e6, "peak": peaks["bf16_tflops"], "frac": fl / us / 1e6 / peaks["bf16_tflops"],
+                             "duration_us_per_launch": us / len(own), "peak_source": src + " (burst: kernel timed alone)",
+                             "timed": "live: graph of 20 back-to-back launches per shape on one stream, L2-warm",
+                             "note": "batch-1 shapes fill 42-126 of 148 SMs for ~10 us: latency-bound"},
+                "note": "duration_us_per_launch = wall time x streams / launches (launches of different frames overlap); the same kernel at batch 8 is in large4k.roofline"}
 
     line = {
         "metric": METRIC, "value": dv["fps"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": B.warmup,
@@ -481,7 +502,7 @@ def main():
     # tail of the line carries the 1080p and the 4K numbers side by side
     l4 = line.get("large4k")
     line["e2e"]["legs"] = {"e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"], "serial_ms_per_frame_device": ms_serial / n_serial, "serial_ms_per_frame_e2e": ms_serial_e2e / n_serial}
-    line["roofline"]["others"] = {"warp_1080p_hbm_frac": roofline_warp["frac"], "frame_graph_tensor_frac_in_flight": roofline_net["frac"],
+    line["roofline"]["others"] = {"gemm_m778_alone_tensor_frac_of_burst": roofline["isolated"]["frac"], "warp_1080p_hbm_frac": roofline_warp["frac"], "frame_graph_tensor_frac_in_flight": roofline_net["frac"],
                                   "frame_graph_tensor_frac_alone": roofline_net["isolated"]["frac"]}
     if l4:
         line["e2e"]["legs"].update({"large4k_value": l4["value"], "large4k_e2e_fp32": l4["e2e"]["value"], "large4k_e2e_u8": l4["e2e_u8"]["value"], "large4k_e2e_nv12": l4["e2e_nv12"]["value"]})
@@ -773,6 +794,62 @@ def gemm_rooflines(dev, peaks, src, shapes="base"):
                     "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "duration_us": us,
                     "peak_source": src + " (burst)", "timed": "graph of %d back-to-back launches, CUDA events on its stream, L2-warm" % iters})
     return out
+
+
+def gemm_in_flight(dev, peaks, src, shapes="base", streams=8, reps=5):
+    """The dominant kernel as it runs in the headline timed region: `streams` frames in flight, each issuing the encoder layer's four
+    GEMMs back to back with the throughput-policy tiles.  Every stream replays a CUDA graph of `reps` layers; wall time between two
+    events that bracket all streams.  achieved = total algorithmic FLOPs / wall time = FLOPs per launch / (wall time x streams / launches)."""
+    import torch
+    from desktop2stereo_b200 import _lib
+    L = _lib.lib()
+    table = {"base": [(778, 2304, 768, False, 0), (778, 768, 768, True, 0), (778, 3072, 768, False, 1), (778, 768, 3072, True, 0)]}[shapes]
+    _lib.check(L.d2s_debug_set_gemm_policy(1), "d2s_debug_set_gemm_policy")
+    try:
+        sts = [torch.cuda.Stream(dev) for _ in range(streams)]
+        graphs, keep = [], []
+        for st in sts:
+            ops = []
+            for (M, N, K, x32, act) in table:
+                A = torch.randn(M, K, device=dev).half(); Bw = torch.randn(N, K, device=dev).half() * (K ** -0.5); bias = torch.randn(N, device=dev)
+                C = torch.empty(M, N, device=dev, dtype=torch.float16); X = torch.zeros(M, N, device=dev)
+                keep.append((A, Bw, bias, C, X))
+                ops.append((A, Bw, bias, None if x32 else C, M, N, K, act, X if x32 else None))
+
+            def layer(ops=ops):
+                for (A, Bw, bias, C, M, N, K, act, X) in ops:
+                    _lib.check(L.d2s_debug_gemm(A.data_ptr(), Bw.data_ptr(), bias.data_ptr(), C.data_ptr() if C is not None else None, M, N, K, act,
+                                                X.data_ptr() if X is not None else None, torch.cuda.current_stream(dev).cuda_stream))
+            with torch.cuda.stream(st):
+                layer(); st.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    for _ in range(reps):
+                        layer()
+                g.replay(); st.synchronize()
+            graphs.append(g)
+        main = torch.cuda.current_stream(dev)
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        s_.record(main)
+        for st, g in zip(sts, graphs):
+            st.wait_event(s_)
+            with torch.cuda.stream(st):
+                g.replay(); g.replay()
+        for st in sts:
+            main.wait_stream(st)
+        e_.record(main)
+        torch.cuda.synchronize(dev)
+    finally:
+        _lib.check(L.d2s_debug_set_gemm_policy(0), "d2s_debug_set_gemm_policy")
+    us = s_.elapsed_time(e_) * 1e3
+    launches = streams * 2 * reps * len(table)
+    fl = streams * 2 * reps * sum(2.0 * M * N * K for (M, N, K, _, _) in table)
+    tf = fl / us / 1e6
+    return {"achieved": tf, "frac": tf / peaks["bf16_tflops_sustained"], "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "launches": launches,
+            "streams": streams, "wall_us": us, "flops_per_launch": fl / launches, "duration_us_per_launch": us * streams / launches,
+            "peak_source": src + " (sustained: a long run of overlapping launches)",
+            "timed": f"live: {streams} streams x graphs of {2 * reps} encoder layers (4 GEMMs each, throughput-policy tiles), CUDA events around all streams"}
 
 
 def load_peaks():

@@ -107,6 +107,7 @@ SYMBOLS = {
     "d2s_pipe_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "d2s_pipe_slot_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "d2s_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "d2s_debug_set_gemm_policy": (C.c_int, [C.c_int]),
     "d2s_debug_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "d2s_debug_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -24,6 +24,14 @@ static int launch_with_scratch(GemmPlan &p, cudaStream_t st) {
     return rc;
 }
 
+// tile policy of the plans d2s_debug_gemm builds on this thread (enum d2s_policy): lets tests / bench time the GEMM kernel with the
+// throughput-policy tiles the pipeline's plans use when several frames are in flight
+extern "C" int d2s_debug_set_gemm_policy(int policy) {
+    D2S_REQUIRE(policy == D2S_POLICY_LATENCY || policy == D2S_POLICY_THROUGHPUT, "d2s_debug_set_gemm_policy: policy %d", policy);
+    gemm_set_plan_policy(policy);
+    return D2S_OK;
+}
+
 extern "C" int d2s_debug_gemm(const void *A, const void *Bw, const float *bias, void *C, int M, int N, int K, int act,
                               float *x32_accumulate, d2s_stream_t stream) {
     D2S_REQUIRE(A && Bw && (C || x32_accumulate), "d2s_debug_gemm: null argument");

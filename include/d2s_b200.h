@@ -268,6 +268,7 @@ int d2s_debug_gemm(const void *A, const void *Bw, const float *bias, void *C, in
                    float *x32_accumulate, d2s_stream_t stream);
 int d2s_debug_conv3x3(const void *A, const void *Wt, const float *bias, void *C, int B, int H, int W, int Cp, int N, int act,
                       const void *res1, void *c_relu, d2s_stream_t stream);
+int d2s_debug_set_gemm_policy(int policy); /* enum d2s_policy for the plans d2s_debug_gemm builds on the calling thread */
 int d2s_debug_attention(const void *qkv, void *out, int B, int N, int D, int heads, d2s_stream_t stream);
 /* 1: d2s_make_sbs always takes the generic (output-centric) kernel — tests compare it with the shared-memory fast path */
 int d2s_debug_force_generic_warp(int on);

@@ -142,8 +142,9 @@ def test_vda_policy_switch_keeps_the_window(cuda_device):
         got.append(eng(frames[t]).clone())
     for t in range(3):
         assert torch.equal(got[t], want[t])
-    for t in range(3, 6):      # different tile shapes: equal to fp16 rounding, and clearly NOT a restarted video
-        assert _rel(got[t], want[t]) <= 2e-3, (t, _rel(got[t], want[t]))
+    for t in range(3, 6):      # different tile shapes and attention kernel: two fp16 evaluations of the same network, each within ~2.5e-3 of
+        # the fp32 oracle (see the parity tests), so within their sum of each other — and clearly NOT a restarted video (below)
+        assert _rel(got[t], want[t]) <= 5e-3, (t, _rel(got[t], want[t]))
     first = want[0]
     assert _rel(got[3], first) > 10 * _rel(got[3], want[3])
     # release_stream drops plans + state of the current stream: the next frame is a first frame again
