@@ -68,3 +68,57 @@ def test_checkpoint_loaders_round_trip(tmp_path):
     torch.save(sd, str(tmp_path / "video_depth_anything_vits.pth"))
     blob2, cfg2 = load_vda_checkpoint(str(tmp_path / "video_depth_anything_vits.pth"), "vits")
     assert cfg2.temporal == 1 and np.array_equal(blob2, pack_vda_state_dict(sd, config_for_vda("vits")))
+
+
+def test_hf_snapshot_written_by_save_pretrained(tmp_path):
+    """the loader must meet a snapshot as transformers itself writes it (config.json + model.safetensors with the real
+    on-disk key names and dtypes), in fp32, fp16 and bf16 (numpy has no bfloat16: the loader reads through torch)."""
+    from desktop2stereo_b200.checkpoints import load_hf_checkpoint
+    m = make_hf_model("Small", 2, TINY_CFG)
+    want_cfg = config_from_hf(m.config)
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        d = tmp_path / str(dt).split(".")[-1]
+        mm = make_hf_model("Small", 2, TINY_CFG).to(dt)
+        mm.save_pretrained(str(d))                      # what `AutoModelForDepthEstimation.from_pretrained` reads (depth.py:1649-1662)
+        assert (d / "config.json").exists() and any(f.name.endswith(".safetensors") for f in d.iterdir())
+        blob, cfg = load_hf_checkpoint(str(d))
+        want = pack_state_dict({k: v.to(dt).float() for k, v in m.state_dict().items()}, want_cfg)
+        assert blob.dtype == np.float32 and np.array_equal(blob, want), dt
+        assert (cfg.hidden, cfg.layers, cfg.heads, list(cfg.out_indices), list(cfg.neck), cfg.fusion, cfg.metric) == \
+               (want_cfg.hidden, want_cfg.layers, want_cfg.heads, list(want_cfg.out_indices), list(want_cfg.neck), want_cfg.fusion, want_cfg.metric)
+
+
+def test_vda_checkpoint_from_the_reference_module(tmp_path):
+    """The .pth the reference loads with strict=True (depth.py:885-901) has exactly the keys of its own VideoDepthAnything module:
+    build that module from the UNMODIFIED reference tree, save its state_dict, and check that the loader consumes every tensor
+    (names, shapes) and packs the same blob as the synthetic state dict of identical values."""
+    import os
+    import sys
+    import types
+    from oracle.ref_harness import REFERENCE_ROOT
+    if not os.path.isdir(REFERENCE_ROOT):
+        pytest.skip("reference tree not present (GPU box)")
+    from desktop2stereo_b200.checkpoints import load_vda_checkpoint
+    from desktop2stereo_b200.synth import VDA_ENCODERS, param_shapes
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    if "easydict" not in sys.modules:      # dpt_temporal.py:19 imports easydict (absent here): attribute-dict stub
+        ed = types.ModuleType("easydict")
+
+        class EasyDict(dict):
+            def __init__(self, **kw):
+                super().__init__(**kw)
+                self.__dict__ = self
+        ed.EasyDict = EasyDict
+        sys.modules["easydict"] = ed
+    from models.video_depth_anything.vda2_s import VideoDepthAnything
+    enc = VDA_ENCODERS["vits"]
+    torch.manual_seed(0)
+    ref = VideoDepthAnything(encoder="vits", features=enc["features"], out_channels=enc["out_channels"]).eval()
+    sd = ref.state_dict()
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in param_shapes("vits")]   # names AND shapes, in module order
+    path = tmp_path / "video_depth_anything_vits.pth"
+    torch.save(sd, str(path))
+    blob, cfg = load_vda_checkpoint(str(path), "vits")
+    assert cfg.temporal == 1 and np.array_equal(blob, pack_vda_state_dict({k: v.clone() for k, v in sd.items()}, config_for_vda("vits")))
+    assert np.isfinite(blob).all()
