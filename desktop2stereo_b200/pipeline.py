@@ -55,6 +55,7 @@ class _Pipe:
         c.streams = B = owner.streams
         c.out_nv12 = int(owner.out_format == "nv12")
         self.handle = C.c_void_p()
+        self.engine = engine                 # the pipe borrows the engine's plans: keep it alive for as long as the pipe lives
         self.device, self.host_io, self.L = owner.device, host_io, L
         with torch.cuda.device(self.device):
             _lib.check(L.d2s_pipe_create(engine._h, C.byref(c), C.byref(self.handle)), "d2s_pipe_create")
@@ -84,6 +85,7 @@ class _Pipe:
             self.host_in, self.host_out, self.dev_out, self.dev_depth, self.streams = [], [], [], [], []
             self.L.d2s_pipe_destroy(self.handle)
             self.handle = None
+            self.engine = None
 
 
 class _DevMem:

@@ -245,6 +245,8 @@ typedef struct d2s_pipe_config {
                                      them as one batch (BASELINE configs 3/5: 8 x 4K), each stream keeps its own DepthStabilizer state */
     int32_t reserved[1];
 } d2s_pipe_config;
+/* Host-synchronous (allocates the slots, builds their plans, captures their graphs).  The pipe borrows `engine`: destroy the pipe
+ * before the engine. */
 int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2s_pipe_handle *out);
 int d2s_pipe_destroy(d2s_pipe_handle p);
 /* frame_bytes / out_bytes are per stream (one frame); a slot's buffers hold `streams` of them back to back */

@@ -58,3 +58,15 @@ def test_single_process_is_identity():
     assert got is b and cfg == "{}"
     assert list(sharding.frames_for_rank(5, 0, 1)) == [0, 1, 2, 3, 4]
     assert sharding.max_over_ranks(3.5) == 3.5
+
+
+def test_numa_binding_helpers():
+    """bind_to_gpu_numa never raises (a box without CUDA / sysfs NUMA data stays unbound) and the cpulist parser handles ranges"""
+    from desktop2stereo_b200.sharding import _parse_cpulist, bind_to_gpu_numa, streams_for_rank
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and _parse_cpulist("") == []
+    info = bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and "bound" in info
+    # configs[4]: 8 streams over G ranks, every stream on exactly one rank
+    for world in (1, 2, 4, 8):
+        owned = [s for r in range(world) for s in streams_for_rank(8, r, world)]
+        assert sorted(owned) == list(range(8)) and len(streams_for_rank(8, 0, world)) == 8 // world
