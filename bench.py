@@ -543,7 +543,7 @@ def large4k_block(B, args):
     frames = [torch.randint(0, 256, (S, h, w, 4), generator=g, dtype=torch.uint8, device=dev) for _ in range(RING)]
     host_frames = [f.cpu().pin_memory() for f in frames]
     steps = max(4, min(args.steps // 8, 16))    # a step = one frame of each of the 8 streams
-    slots = 2
+    slots = int(os.environ.get("D2S_BENCH_L4K_SLOTS", "2"))
     legs = pipe_legs(B, depth, frames, host_frames, h, w, S, slots, steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8)])
     dv, e2e, e2e8, e2en = legs["device"], legs["e2e"], legs["e2e_u8"], legs["e2e_nv12"]
     gflop = S * model_flops(cfg, 294, 518) / 1e9
