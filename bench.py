@@ -575,7 +575,7 @@ def large4k_block(B, args):
         from desktop2stereo_b200.sharding import streams_for_rank
         mine = streams_for_rank(8, rank, world)
         sl = len(mine)
-        f5 = [f[:sl].contiguous() for f in frames]
+        f5 = [(f[:sl] if sl > 1 else f[0]).contiguous() for f in frames]      # one stream per GPU: plain [h, w, 4] frames
         h5 = [f.cpu().pin_memory() for f in f5]
         l5 = pipe_legs(B, depth, f5, h5, h, w, sl, 2, 8, [("e2e", torch.float32), ("e2e_u8", torch.uint8)])
         # every rank runs 8 steps of its own streams; whole job = 64 frames per region
