@@ -166,7 +166,7 @@ def run_reference(args):
     if args.impl == "reference-cuda":
         import torch
         dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-        fps, dt = cuda_reference_fps(args.steps, max(args.warmup, 3), dev)
+        fps, dt = cuda_reference_fps(args.steps, max(args.warmup, 10), dev)   # cuDNN autotuning and clock ramp-up settle within ~10 frames
         extra = {"impl": "reference-cuda", "dtype": "fp16 autocast (torch CUDA: cuBLAS/cuDNN/SDPA + ATen)",
                  "reference_cuda": {"value": fps, "unit": "frames/s", "kind": "port", "sample": f"{args.steps} frames, one at a time, H2D + .cpu() per frame"},
                  "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": H * W * 4, "d2h_bytes_per_step": H * 2 * W * 3 * 4}}
