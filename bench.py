@@ -246,8 +246,48 @@ class Bench:
         return {"ms": ms[len(ms) // 2], "min": ms[0], "max": ms[-1], "repeats": len(ms)}
 
 
+def desktop_like_frames(torch, n, streams, h, w, seed):
+    """BGRA frames with the statistics of desktop content (flat panels, gradients, 1-pixel text-like strokes, one noisy 'video'
+    window): the size of a JPEG stream depends on content, so the compact-output legs are measured on this AND on uniform noise.
+    Built at 1080p and tiled to larger sizes.  Pinned host tensors [streams, h, w, 4] (or [h, w, 4])."""
+    import numpy as np
+    bh, bw = min(h, 1080), min(w, 1920)
+
+    def one(sd):
+        rng = np.random.default_rng(sd)
+        yy, xx = np.mgrid[0:bh, 0:bw].astype(np.float32)
+        img = np.stack([40 + 60 * xx / bw, 50 + 80 * yy / bh, 90 + 40 * (xx + yy) / (bh + bw)], -1)
+        for _ in range(24):
+            y0, x0 = int(rng.integers(0, bh - 8)), int(rng.integers(0, bw - 8))
+            img[y0:y0 + int(rng.integers(8, bh // 3)), x0:x0 + int(rng.integers(8, bw // 3))] = rng.integers(0, 256, 3)
+        panel = img[bh // 8:bh // 8 + bh // 4, bw // 8:bw // 8 + bw // 3]
+        panel[:] = 235
+        mask = rng.random(panel.shape[:2]) < 0.18
+        mask[::3] = False
+        panel[mask] = 20
+        vy, vx, vh, vw = bh // 2, bw // 2, bh // 3, bw // 3
+        tex = 128 + 60 * np.sin(xx[vy:vy + vh, vx:vx + vw] / 9.0) * np.cos(yy[vy:vy + vh, vx:vx + vw] / 7.0)
+        img[vy:vy + vh, vx:vx + vw] = tex[..., None] + rng.normal(0, 6, (vh, vw, 3))
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        img = np.tile(img, (-(-h // bh), -(-w // bw), 1))[:h, :w]
+        return np.concatenate([img[..., ::-1], np.full((h, w, 1), 255, np.uint8)], -1)
+    base = [one(seed + i) for i in range(4)]
+    out = []
+    for i in range(n):
+        f = np.stack([base[(i + b) % 4] for b in range(streams)]) if streams > 1 else base[i % 4]
+        out.append(torch.from_numpy(np.ascontiguousarray(f)).pin_memory())
+    return out
+
+
+def jpeg_leg(d, **kw):
+    keys = ("h2d_bytes_per_step", "d2h_bytes_per_step", "pcie_gbs_per_gpu", "jpeg_bytes_per_frame", "jpeg_bytes_per_pixel", "content", "jpeg")
+    return dict({"value": d["fps"], "unit": "frames/s"}, **{k: d[k] for k in keys}, **kw)
+
+
 def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, out_dtypes, want_device=True):
-    """device-resident and host-buffer legs of one workload through StereoPipeline; a step = one submit = `streams` frames"""
+    """device-resident and host-buffer legs of one workload through StereoPipeline; a step = one submit = `streams` frames.
+    Legs named e2e_jpeg*: out_format='jpeg' (the whole JPEG encode on the device; d2h bytes = the measured stream sizes, rounded up
+    as the pipe's adaptive copy does); *_desktop: desktop-like frames instead of uniform noise."""
     import numpy as np
     torch = B.torch
     from desktop2stereo_b200 import _lib
@@ -280,23 +320,39 @@ def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, ou
                              stage_ms=dict(zip(["process", "resize+network+postprocess", "upsample+warp"], np.median(st, 0).tolist())))
         pipe.close()
     for name, odt in out_dtypes:
-        fmt = "nv12" if name.endswith("nv12") else "rgb"
+        fmt = "jpeg" if "jpeg" in name else "nv12" if name.endswith("nv12") else "rgb"
+        src = desktop_like_frames(torch, ring_h, streams, h, w, SEED + 7 * B.rank) if name.endswith("_desktop") else frames_host
         if fmt == "nv12":
             oshape = ((streams,) if streams > 1 else ()) + (h * 3 // 2, 2 * w)
         pipe = StereoPipeline(depth_slots=slots, display_mode=DISPLAY_MODE, depth_ratio=DEPTH_RATIO, out_dtype=odt, streams=streams, out_format=fmt)
+        sizes = []
 
-        def run_host(idx, p=pipe):
+        def run_host(idx, p=pipe, src=src, fmt=fmt):
             r = None
-            for r in p.run((frames_host[i % ring_h] for i in idx), host=True):   # pinned host frames -> H2D inside the timed region
-                pass
+            for r in p.run((src[i % ring_h] for i in idx), host=True):   # pinned host frames -> H2D inside the timed region
+                if fmt == "jpeg":
+                    sizes.extend(len(x) for x in (r if streams > 1 else [r]))
             return r
         r = run_host(range(warm))
-        assert tuple(r.shape) == oshape and r.dtype == {torch.float32: np.float32, torch.uint8: np.uint8}[odt]
+        if fmt == "jpeg":
+            for x in (r if streams > 1 else [r]):
+                assert bytes(x[:3]) == b"\xff\xd8\xff" and bytes(x[-2:]) == b"\xff\xd9"
+        else:
+            assert tuple(r.shape) == oshape and r.dtype == {torch.float32: np.float32, torch.uint8: np.uint8}[odt]
+        sizes.clear()
         t = B.timed(run_host, steps)
         es = 4 if odt == torch.float32 else 1
-        h2d, d2h = fpp * h * w * 4, (fpp * h * 2 * w * 3 * es if fmt == "rgb" else fpp * h * 2 * w * 3 // 2)
+        h2d = fpp * h * w * 4
+        extra = {}
+        if fmt == "jpeg":
+            mean = float(np.mean(sizes))
+            d2h = int(fpp * ((int(mean * 1.25) + 16 + 65535) // 65536) * 65536)
+            extra = {"jpeg_bytes_per_frame": mean, "jpeg_bytes_per_pixel": mean / (h * 2 * w), "content": "desktop-like" if name.endswith("_desktop") else "uniform noise",
+                     "jpeg": "quality 90, restart interval 2 MCUs; byte-identical to cv2.imencode (tests/test_jpeg_gpu.py)"}
+        else:
+            d2h = fpp * h * 2 * w * 3 * es if fmt == "rgb" else fpp * h * 2 * w * 3 // 2
         fps = B.world * steps * fpp / (t["ms"] / 1e3)
-        res[name] = dict(t, fps=fps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, pcie_gbs_per_gpu=(h2d + d2h) * fps / fpp / B.world / 1e9)
+        res[name] = dict(t, fps=fps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, pcie_gbs_per_gpu=(h2d + d2h) * fps / fpp / B.world / 1e9, **extra)
         pipe.close()
     return res
 
@@ -399,7 +455,8 @@ def main():
     serial_e2e(range(B.warmup))
     ms_serial_e2e = B.region(serial_e2e, n_serial)
 
-    legs = pipe_legs(B, depth, frames, host_frames, H, W, 1, args.slots, args.steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8)])
+    legs = pipe_legs(B, depth, frames, host_frames, H, W, 1, args.slots, args.steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8),
+                                                                                    ("e2e_jpeg", torch.uint8), ("e2e_jpeg_desktop", torch.uint8)])
     dv, e2e, e2e8, e2en = legs["device"], legs["e2e"], legs["e2e_u8"], legs["e2e_nv12"]
     host_bw = host_copy_bandwidth(B)
 
@@ -466,6 +523,8 @@ def main():
             "e2e_nv12": {"value": e2en["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2en["h2d_bytes_per_step"], "d2h_bytes_per_step": e2en["d2h_bytes_per_step"],
                          "pcie_gbs_per_gpu": e2en["pcie_gbs_per_gpu"],
                          "note": "same loop, NV12 frame (libjpeg colour conversion + 4:2:0 on the device, 1.5 B/px): 8x fewer bytes than float32"},
+            "e2e_jpeg": jpeg_leg(legs["e2e_jpeg"], note="same loop, the whole JPEG encode on the device (replaces cv2.imencode, streamer.py:250-256)"),
+            "e2e_jpeg_desktop": jpeg_leg(legs["e2e_jpeg_desktop"]),
             "serial": {"note": "the drop-in calls one frame at a time on one stream (latency view); stage_ms = medians", "steps": n_serial,
                        "fps_device": world * n_serial / (ms_serial / 1e3), "fps_e2e": world * n_serial / (ms_serial_e2e / 1e3),
                        "ms_per_frame_device": ms_serial / n_serial, "ms_per_frame_e2e": ms_serial_e2e / n_serial, "stage_ms": serial_stage_ms},
@@ -519,8 +578,10 @@ def main():
             line["cpu_baseline"]["reference_torch_cuda_same_gpu"] = line["reference_cuda"]["value"]
     if "vda1080" in line:
         line["e2e"]["legs"].update({"vda1080_value": line["vda1080"]["value"], "vda1080_e2e_fp32": line["vda1080"]["e2e"]})
-    line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"]},
-                       "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"], "e2e_nv12": l4["e2e_nv12"]["value"]} if l4 else None),
+    line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"],
+                                    "e2e_jpeg_noise": legs["e2e_jpeg"]["fps"], "e2e_jpeg_desktop": legs["e2e_jpeg_desktop"]["fps"]},
+                       "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"], "e2e_nv12": l4["e2e_nv12"]["value"],
+                                    "e2e_jpeg_desktop": l4["e2e_jpeg_desktop"]["value"]} if l4 else None),
                        "vda1080": ({"value": line["vda1080"]["value"], "e2e_fp32": line["vda1080"]["e2e"]} if "vda1080" in line else None),
                        "reference_cuda_base1080": line.get("reference_cuda", {}).get("value"), "unit": "frames/s", "n_gpus": world}
     if rank == 0:
@@ -544,7 +605,8 @@ def large4k_block(B, args):
     host_frames = [f.cpu().pin_memory() for f in frames]
     steps = max(4, min(args.steps // 8, 16))    # a step = one frame of each of the 8 streams
     slots = int(os.environ.get("D2S_BENCH_L4K_SLOTS", "2"))
-    legs = pipe_legs(B, depth, frames, host_frames, h, w, S, slots, steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8)])
+    legs = pipe_legs(B, depth, frames, host_frames, h, w, S, slots, steps, [("e2e", torch.float32), ("e2e_u8", torch.uint8), ("e2e_nv12", torch.uint8),
+                                                                            ("e2e_jpeg_desktop", torch.uint8)])
     dv, e2e, e2e8, e2en = legs["device"], legs["e2e"], legs["e2e_u8"], legs["e2e_nv12"]
     gflop = S * model_flops(cfg, 294, 518) / 1e9
     step_ms = dv["ms"] / steps
@@ -562,6 +624,7 @@ def large4k_block(B, args):
                       "pcie_gbs_per_gpu": e2e8["pcie_gbs_per_gpu"]},
            "e2e_nv12": {"value": e2en["fps"], "unit": "frames/s", "h2d_bytes_per_step": e2en["h2d_bytes_per_step"], "d2h_bytes_per_step": e2en["d2h_bytes_per_step"],
                         "pcie_gbs_per_gpu": e2en["pcie_gbs_per_gpu"]},
+           "e2e_jpeg_desktop": jpeg_leg(legs["e2e_jpeg_desktop"]),
            "target": {"north_star": ">= 60 frames/s end-to-end 4K depth + Full-SBS on 1 x B200", "met_fp32": e2e["fps"] / world >= 60, "met_u8": e2e8["fps"] / world >= 60},
            "roofline": {"kernel": "gemm_tc_persistent_kernel (tcgen05, cta_group::2), the 4 GEMMs of one ViT-L encoder layer at M = 6224", "bound": "tensor",
                         "achieved": fl / us / 1e6, "peak": B.peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / B.peaks["bf16_tflops"],

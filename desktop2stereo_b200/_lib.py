@@ -68,8 +68,9 @@ class PipeConfig(C.Structure):
                 ("subsample_cap", C.c_int32), ("gamma", C.c_float), ("foreground_scale", C.c_float), ("aa_strength", C.c_float),
                 ("use_temporal_smooth", C.c_int32), ("ema_alpha", C.c_float),
                 ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
-                ("display_mode", C.c_int32), ("fill_16_9", C.c_int32), ("out_dtype", C.c_int32), ("out_nv12", C.c_int32),
-                ("slots", C.c_int32), ("host_io", C.c_int32), ("streams", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("display_mode", C.c_int32), ("fill_16_9", C.c_int32), ("out_dtype", C.c_int32), ("out_format", C.c_int32),
+                ("slots", C.c_int32), ("host_io", C.c_int32), ("streams", C.c_int32),
+                ("jpeg_quality", C.c_int32), ("jpeg_restart_interval", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 # every symbol include/d2s_b200.h declares: name -> (restype, argtypes)
@@ -94,6 +95,9 @@ SYMBOLS = {
     "d2s_postprocess": (C.c_int, [C.POINTER(PostParams), C.c_void_p]),
     "d2s_overlay_fps": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_char_p, C.c_void_p]),
     "d2s_rgb_to_nv12": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "d2s_jpeg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "d2s_jpeg_max_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "d2s_jpeg_encode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "d2s_dibr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "d2s_dibr_out_shape": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "d2s_make_sbs_dibr": (C.c_int, [C.POINTER(DibrParams), C.c_void_p]),

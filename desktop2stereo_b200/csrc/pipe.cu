@@ -13,6 +13,8 @@
 // weight tables of both resizes are input-independent and are built once at creation (the per-call entry points rebuild them).
 // Arithmetic is that of d2s_process / d2s_preprocess / d2s_infer / d2s_postprocess / d2s_make_sbs — the same kernels, launched
 // through the same code — so a frame through the pipe equals the same frame through the five calls, bit for bit.
+#include <algorithm>
+#include <cstddef>
 #include <vector>
 
 #include "engine.cuh"
@@ -30,7 +32,9 @@ struct PipeSlot {
     void *ws_proc = nullptr, *ws_pre = nullptr, *ws_post = nullptr;
     void *d_depth = nullptr;         // [h,w] fp16: predict_depth's return value
     void *d_out = nullptr;           // packed stereo frame
-    void *d_nv12 = nullptr;          // cfg.out_nv12: the frame the caller receives ([oh * 3 / 2, ow] u8 per stream)
+    void *d_enc = nullptr;           // cfg.out_format != PACKED: what the caller receives (NV12 frame / d2s_pipe_jpeg_frame per stream)
+    void *ws_jpeg = nullptr;         // D2S_OUT_JPEG: one d2s_jpeg_encode workspace per stream
+    size_t copied = 0;               // D2S_OUT_JPEG with host_io: bytes per stream the submit copied to the host
     void *h_in = nullptr, *h_out = nullptr;
     ShapePlan *plan = nullptr;
     cudaGraphExec_t gA = nullptr, gB = nullptr;
@@ -56,6 +60,8 @@ struct d2s_pipe {
     int oh, ow;        // packed stereo frame
     size_t frame_bytes, out_bytes, res_bytes, rgb_es, out_es;   // out: the packed RGB frame, res: what the caller receives (per stream)
     size_t ws_proc_bytes, ws_pre_bytes, ws_post_bytes;
+    size_t ws_jpeg_bytes = 0, jpeg_head = 0;  // D2S_OUT_JPEG: workspace per stream; bytes per stream the next submit copies to the host
+    int jpeg_quality = 90, jpeg_ri = 2;
     void *ema_state = nullptr;               // [Hm,Wm] fp16, NaN = unset (d2s_post_params.ema_valid == 2)
     cudaEvent_t last_ema = nullptr;          // EMA event of the most recently submitted frame
     bool trace = false;
@@ -65,6 +71,9 @@ struct d2s_pipe {
 namespace d2s {
 
 int rgb_to_nv12_launch(const uint8_t *rgb, long long pitch, int h, int w, uint8_t *yp, uint8_t *uvp, cudaStream_t stream);   // nv12.cu
+int jpeg_encode_launch(const uint8_t *rgb, long long pitch, int h, int w, int quality, int ri, uint8_t *out, size_t capacity, uint32_t *size_out,
+                       void *workspace, size_t workspace_bytes, cudaStream_t stream);                                          // jpeg.cu
+size_t jpeg_workspace(int h, int w, int ri);
 
 __global__ void pipe_join_kernel(int) {}      // a single kernel predecessor for whatever follows a join (programmatic launch edges need one)
 
@@ -132,7 +141,11 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     D2S_CHECK_CUDA(cudaMalloc(&s.ws_post, B * p->ws_post_bytes));     // (one per stream: its blur-x result waits there for the EMA step)
     D2S_CHECK_CUDA(cudaMalloc(&s.d_depth, (size_t)B * p->h * p->w * 2));
     D2S_CHECK_CUDA(cudaMalloc(&s.d_out, B * p->out_bytes));
-    if (c.out_nv12) D2S_CHECK_CUDA(cudaMalloc(&s.d_nv12, B * p->res_bytes));
+    if (c.out_format != D2S_OUT_PACKED) D2S_CHECK_CUDA(cudaMalloc(&s.d_enc, B * p->res_bytes));
+    if (c.out_format == D2S_OUT_JPEG) {
+        D2S_CHECK_CUDA(cudaMalloc(&s.ws_jpeg, B * p->ws_jpeg_bytes));
+        D2S_CHECK_CUDA(cudaMemsetAsync(s.d_enc, 0, B * p->res_bytes, s.stream));
+    }
     if (c.host_io) {
         D2S_CHECK_CUDA(cudaHostAlloc(&s.h_in, B * p->frame_bytes, cudaHostAllocDefault));
         D2S_CHECK_CUDA(cudaHostAlloc(&s.h_out, B * p->res_bytes, cudaHostAllocDefault));
@@ -156,13 +169,16 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
 
     const bool split = c.use_temporal_smooth != 0;
-    auto warp_and_pack = [&](int b, cudaStream_t st) -> int {      // stereo warp (+ the NV12 stages of the output encoder)
+    auto warp_and_pack = [&](int b, cudaStream_t st) -> int {      // stereo warp (+ the output encoder: NV12 stages, or the whole JPEG)
         d2s_warp_params wp; fill_warp(p, s, b, &wp);
         int r = d2s_make_sbs(&wp, st);
-        if (!r && c.out_nv12) {
-            uint8_t *nv = (uint8_t *)s.d_nv12 + (size_t)b * p->res_bytes;
-            r = rgb_to_nv12_launch((const uint8_t *)s.d_out + (size_t)b * p->out_bytes, (long long)p->ow * 3, p->oh, p->ow, nv, nv + (size_t)p->oh * p->ow, st);
-        }
+        const uint8_t *packed = (const uint8_t *)s.d_out + (size_t)b * p->out_bytes;
+        uint8_t *enc = (uint8_t *)s.d_enc + (size_t)b * p->res_bytes;
+        if (!r && c.out_format == D2S_OUT_NV12) r = rgb_to_nv12_launch(packed, (long long)p->ow * 3, p->oh, p->ow, enc, enc + (size_t)p->oh * p->ow, st);
+        if (!r && c.out_format == D2S_OUT_JPEG)
+            r = jpeg_encode_launch(packed, (long long)p->ow * 3, p->oh, p->ow, p->jpeg_quality, p->jpeg_ri, enc + offsetof(d2s_pipe_jpeg_frame, data),
+                                   p->res_bytes - offsetof(d2s_pipe_jpeg_frame, data), (uint32_t *)enc, (char *)s.ws_jpeg + (size_t)b * p->ws_jpeg_bytes,
+                                   p->ws_jpeg_bytes, st);
         return r;
     };
     // run body(b, stream) for every stream of the step: in line for one stream, as parallel branches of the capture otherwise
@@ -215,7 +231,7 @@ static void free_slot(PipeSlot &s) {
     if (s.gB) cudaGraphExecDestroy(s.gB);
     if (s.graphA) cudaGraphDestroy(s.graphA);
     if (s.graphB) cudaGraphDestroy(s.graphB);
-    for (void *q : {(void *)s.d_frame, s.d_rgb, s.ws_proc, s.ws_pre, s.ws_post, s.d_depth, s.d_out, s.d_nv12}) if (q) cudaFree(q);
+    for (void *q : {(void *)s.d_frame, s.d_rgb, s.ws_proc, s.ws_pre, s.ws_post, s.d_depth, s.d_out, s.d_enc, s.ws_jpeg}) if (q) cudaFree(q);
     if (s.h_in) cudaFreeHost(s.h_in);
     if (s.h_out) cudaFreeHost(s.h_out);
     for (cudaEvent_t e : {s.done, s.ema_ev, s.in_ev, s.fork_ev, s.t[0], s.t[1], s.t[2], s.t[3]}) if (e) cudaEventDestroy(e);
@@ -254,11 +270,20 @@ extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2
     p->rgb_es = dtype_size(cfg->rgb_dtype); p->out_es = dtype_size(cfg->out_dtype);
     p->frame_bytes = (size_t)cfg->frame_h * cfg->frame_w * cfg->channels;
     p->out_bytes = (size_t)p->oh * p->ow * 3 * p->out_es;
-    p->res_bytes = cfg->out_nv12 ? (size_t)p->oh * p->ow * 3 / 2 : p->out_bytes;
-    if (cfg->out_nv12 && (cfg->out_dtype != D2S_U8 || p->oh % 2 || p->ow % 2)) {
-        rc = set_error(D2S_ERR_INVALID, "d2s_pipe_create: out_nv12 needs out_dtype U8 and an even-sized packed frame (%dx%d)", p->oh, p->ow);
+    p->res_bytes = cfg->out_format == D2S_OUT_PACKED ? p->out_bytes : (size_t)p->oh * p->ow * 3 / 2;
+    if (cfg->out_format < D2S_OUT_PACKED || cfg->out_format > D2S_OUT_JPEG ||
+        (cfg->out_format != D2S_OUT_PACKED && (cfg->out_dtype != D2S_U8 || p->oh % 2 || p->ow % 2))) {
+        rc = set_error(D2S_ERR_INVALID, "d2s_pipe_create: out_format %d needs out_dtype U8 and an even-sized packed frame (%dx%d)", cfg->out_format, p->oh, p->ow);
         delete p;
         return rc;
+    }
+    if (cfg->out_format == D2S_OUT_JPEG) {
+        p->jpeg_quality = cfg->jpeg_quality > 0 ? cfg->jpeg_quality : 90;
+        p->jpeg_ri = cfg->jpeg_restart_interval > 0 ? cfg->jpeg_restart_interval : 2;
+        p->res_bytes = (p->res_bytes + offsetof(d2s_pipe_jpeg_frame, data) + 1024 + 255) & ~(size_t)255;
+        if (d2s_jpeg_workspace_bytes(p->oh, p->ow, p->jpeg_ri) == 0) { delete p; return D2S_ERR_INVALID; }
+        p->ws_jpeg_bytes = (jpeg_workspace(p->oh, p->ow, p->jpeg_ri) + 255) & ~(size_t)255;
+        p->jpeg_head = std::min(p->res_bytes, std::max((size_t)65536, ((size_t)p->oh * p->ow / 4 + 65535) & ~(size_t)65535));
     }
     p->ws_proc_bytes = process_workspace_bytes(cfg->frame_h, cfg->frame_w, p->h, p->w);
     p->ws_pre_bytes = d2s_preprocess_workspace_bytes(p->h, p->w, p->Hm, p->Wm);
@@ -305,7 +330,7 @@ extern "C" int d2s_pipe_slot_buffers(d2s_pipe_handle p, int slot, void **host_in
                                      d2s_stream_t *stream) {
     D2S_REQUIRE(p && slot >= 0 && slot < (int)p->slots.size(), "d2s_pipe_slot_buffers: bad slot");
     const PipeSlot &s = p->slots[slot];
-    if (host_in) *host_in = s.h_in; if (host_out) *host_out = s.h_out; if (dev_in) *dev_in = s.d_frame; if (dev_out) *dev_out = s.d_nv12 ? s.d_nv12 : s.d_out;
+    if (host_in) *host_in = s.h_in; if (host_out) *host_out = s.h_out; if (dev_in) *dev_in = s.d_frame; if (dev_out) *dev_out = s.d_enc ? s.d_enc : s.d_out;
     if (dev_depth) *dev_depth = s.d_depth; if (stream) *stream = s.stream;
     return D2S_OK;
 }
@@ -347,7 +372,10 @@ extern "C" int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d
     }
     g_launch_count.fetch_add(kernels, std::memory_order_relaxed);
     if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[3], st));
-    if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_nv12 ? s.d_nv12 : s.d_out, p->B * p->res_bytes, cudaMemcpyDeviceToHost, st));
+    if (c.host_io && c.out_format == D2S_OUT_JPEG) {      // only as much of every stream's buffer as recent frames needed
+        s.copied = p->jpeg_head;
+        D2S_CHECK_CUDA(cudaMemcpy2DAsync(s.h_out, p->res_bytes, s.d_enc, p->res_bytes, s.copied, p->B, cudaMemcpyDeviceToHost, st));
+    } else if (c.host_io) D2S_CHECK_CUDA(cudaMemcpyAsync(s.h_out, s.d_enc ? s.d_enc : s.d_out, p->B * p->res_bytes, cudaMemcpyDeviceToHost, st));
     D2S_CHECK_CUDA(cudaEventRecord(s.done, st));
     s.busy = true;
     return D2S_OK;
@@ -359,6 +387,20 @@ extern "C" int d2s_pipe_wait(d2s_pipe_handle p, int slot) {
     D2S_REQUIRE(s.busy, "d2s_pipe_wait: slot %d has no frame in flight", slot);
     D2S_CHECK_CUDA(cudaEventSynchronize(s.done));
     s.busy = false;
+    if (p->cfg.host_io && p->cfg.out_format == D2S_OUT_JPEG) {
+        size_t need = 0;
+        for (int b = 0; b < p->B; ++b) {
+            const d2s_pipe_jpeg_frame *f = (const d2s_pipe_jpeg_frame *)((const char *)s.h_out + (size_t)b * p->res_bytes);
+            D2S_REQUIRE(f->size != 0, "d2s_pipe_wait: the JPEG stream of stream %d did not fit %zu bytes", b, p->res_bytes);
+            need = std::max(need, offsetof(d2s_pipe_jpeg_frame, data) + (size_t)f->size);
+        }
+        if (need > s.copied) {        // this frame outgrew the estimate: fetch the tails now
+            D2S_CHECK_CUDA(cudaMemcpy2DAsync((char *)s.h_out + s.copied, p->res_bytes, (const char *)s.d_enc + s.copied, p->res_bytes, need - s.copied, p->B,
+                                             cudaMemcpyDeviceToHost, s.stream));
+            D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
+        }
+        p->jpeg_head = std::min(p->res_bytes, std::max((size_t)65536, (need + need / 4 + 65535) & ~(size_t)65535));
+    }
     return D2S_OK;
 }
 

@@ -53,7 +53,9 @@ class _Pipe:
         c.display_mode, c.fill_16_9 = DISPLAY_MODES[p["display_mode"]], int(bool(p["fill_16_9"]))
         c.out_dtype, c.slots, c.host_io = _TORCH2D2S[owner.out_dtype], owner.n_slots, int(host_io)
         c.streams = B = owner.streams
-        c.out_nv12 = int(owner.out_format == "nv12")
+        c.out_format = {"rgb": 0, "nv12": 1, "jpeg": 2}[owner.out_format]
+        c.jpeg_quality, c.jpeg_restart_interval = int(owner.jpeg_quality), int(owner.jpeg_restart_interval)
+        self.jpeg = owner.out_format == "jpeg"
         self.handle = C.c_void_p()
         self.engine = engine                 # the pipe borrows the engine's plans: keep it alive for as long as the pipe lives
         self.device, self.host_io, self.L = owner.device, host_io, L
@@ -71,7 +73,8 @@ class _Pipe:
             _lib.check(L.d2s_pipe_slot_buffers(self.handle, i, *[C.byref(x) for x in ptr]), "d2s_pipe_slot_buffers")
             hin, hout, _din, dout, ddep, st = [x.value for x in ptr]
             lead = (B,) if B > 1 else ()       # several streams: one frame of each per submit, stacked on a leading axis
-            oshape = (self.oh * 3 // 2, self.ow) if c.out_nv12 else (self.oh, self.ow, 3)
+            # jpeg: the raw d2s_pipe_jpeg_frame bytes of every stream (u32 size, 12 reserved bytes, then the stream)
+            oshape = (ob.value,) if self.jpeg else (self.oh * 3 // 2, self.ow) if c.out_format == 1 else (self.oh, self.ow, 3)
             if host_io:   # numpy views of the library's pinned buffers (no copy)
                 self.host_in.append(np.ctypeslib.as_array((C.c_uint8 * (B * fb.value)).from_address(hin)).reshape(lead + (h0, w0, ch)))
                 raw = np.ctypeslib.as_array((C.c_uint8 * (B * ob.value)).from_address(hout))
@@ -101,16 +104,28 @@ def _device_view(ptr, shape, dtype, device):
         return torch.as_tensor(_DevMem(ptr, shape, typestr), device=device)
 
 
+def _jpeg_streams(buf, streams):
+    """d2s_pipe_jpeg_frame buffers -> the JPEG stream(s) they hold (views; u8)"""
+    def one(b):
+        head = b[:4].cpu().numpy() if isinstance(b, torch.Tensor) else b[:4]
+        return b[16:16 + int(np.frombuffer(head.tobytes(), np.uint32)[0])]
+    return [one(buf[i]) for i in range(streams)] if streams > 1 else one(buf)
+
+
 class StereoPipeline:
     def __init__(self, depth_slots: int = 3, display_mode="Full-SBS", ipd_uv=0.064, depth_ratio=2.0, convergence=0.0,
                  fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None, streams=1,
-                 out_format="rgb"):
+                 out_format="rgb", jpeg_quality=90, jpeg_restart_interval=2):
         """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and the post-process settings live there).
         A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224).
         streams > 1: that many concurrent video streams share the pipeline; every submit takes one frame of each, stacked as
         [streams, h, w, ch] (the network runs them as one batch; each stream has its own DepthStabilizer state).
         out_format="nv12" (with out_dtype=torch.uint8): results are NV12 frames [oh * 3 // 2, ow] u8 — the colour-conversion and
-        4:2:0 stages of the JPEG encoder the reference runs on the host (streamer.py:250-256), done on the device: 1.5 B/px."""
+        4:2:0 stages of the JPEG encoder the reference runs on the host (streamer.py:250-256), done on the device: 1.5 B/px.
+        out_format="jpeg" (with out_dtype=torch.uint8): results are complete JPEG streams (1-D u8 arrays; a list of them when
+        streams > 1), byte-identical to cv2.imencode(".jpg", bgr, [IMWRITE_JPEG_QUALITY, jpeg_quality, IMWRITE_JPEG_RST_INTERVAL,
+        jpeg_restart_interval]) of the u8 frame — MJPEGStreamer's whole encoder loop (streamer.py:231-256) on the device; what
+        crosses PCIe is the compressed stream."""
         d2s_depth._need_init()
         engine = d2s_depth.model_wraper.model
         if getattr(engine.cfg, "temporal", 0) and depth_slots != 1:
@@ -120,9 +135,9 @@ class StereoPipeline:
             raise ValueError(f"display_mode {display_mode!r}")
         self.device = d2s_depth.model_wraper.device if device is None else torch.device(device)
         self.n_slots, self.streams = depth_slots, int(streams)
-        if out_format not in ("rgb", "nv12") or (out_format == "nv12" and out_dtype != torch.uint8):
-            raise ValueError("out_format is 'rgb' or 'nv12' (nv12 needs out_dtype=torch.uint8)")
-        self.out_format = out_format
+        if out_format not in ("rgb", "nv12", "jpeg") or (out_format != "rgb" and out_dtype != torch.uint8):
+            raise ValueError("out_format is 'rgb', 'nv12' or 'jpeg' (nv12 and jpeg need out_dtype=torch.uint8)")
+        self.out_format, self.jpeg_quality, self.jpeg_restart_interval = out_format, jpeg_quality, jpeg_restart_interval
         self.params = dict(ipd_uv=ipd_uv, depth_ratio=depth_ratio, convergence=convergence, fill_16_9=fill_16_9,
                            display_mode=display_mode)
         self.use_temporal_smooth, self.out_dtype, self.target_height = use_temporal_smooth, out_dtype, target_height
@@ -211,9 +226,8 @@ class StereoPipeline:
             ms = (C.c_float * 3)()
             _lib.check(pipe.L.d2s_pipe_slot_times(pipe.handle, slot, ms), "d2s_pipe_slot_times")
             self.trace.append(tuple(ms))
-        if host and pipe.host_io:
-            return pipe.host_out[slot]
-        return pipe.dev_out[slot]
+        out = pipe.host_out[slot] if host and pipe.host_io else pipe.dev_out[slot]
+        return _jpeg_streams(out, self.streams) if pipe.jpeg else out
 
     def depth_of(self, ticket: _Ticket) -> torch.Tensor:
         """The [h,w] fp16 depth map (what predict_depth returns) of a collected frame; valid until the slot is reused."""

@@ -113,6 +113,44 @@ def rgb_to_nv12(rgb_hwc: torch.Tensor, out: torch.Tensor | None = None) -> torch
     return out
 
 
+class JpegEncoder:
+    """Device-side baseline JPEG encoder for packed u8 HWC frames of one size (d2s_jpeg_encode): the encode MJPEGStreamer runs on
+    the host (cv2.imencode, reference streamer.py:250-256), byte-identical to it for the same quality and restart interval.
+    Owns its workspace and output buffer; `encode` is asynchronous on the current stream and returns (stream_buffer, size_tensor);
+    `encode_bytes` synchronises and returns the JPEG as bytes."""
+
+    def __init__(self, h: int, w: int, device, quality: int = 90, restart_interval: int = 4, capacity: int | None = None):
+        L = _lib.lib()
+        self.h, self.w, self.quality, self.restart_interval = int(h), int(w), int(quality), int(restart_interval)
+        ws = L.d2s_jpeg_workspace_bytes(self.h, self.w, self.restart_interval)
+        if ws == 0:
+            raise ValueError(f"JpegEncoder: {L.d2s_last_error().decode('utf-8', 'replace')}")
+        self.device = torch.device(device)
+        self.capacity = int(capacity) if capacity else int(L.d2s_jpeg_max_bytes(self.h, self.w, self.restart_interval))
+        self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
+        self.out = torch.empty(self.capacity, dtype=torch.uint8, device=self.device)
+        self.size = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def encode(self, rgb_hwc: torch.Tensor):
+        _require_cuda(rgb_hwc, "rgb")
+        if rgb_hwc.dtype != torch.uint8 or rgb_hwc.dim() != 3 or rgb_hwc.shape[2] != 3 or rgb_hwc.stride(2) != 1 or rgb_hwc.stride(1) != 3:
+            raise ValueError("JpegEncoder.encode expects a uint8 [h,w,3] tensor with packed pixels")
+        if tuple(rgb_hwc.shape[:2]) != (self.h, self.w):
+            raise ValueError(f"JpegEncoder was built for {self.h}x{self.w}, got {tuple(rgb_hwc.shape[:2])}")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().d2s_jpeg_encode(rgb_hwc.data_ptr(), rgb_hwc.stride(0), self.h, self.w, self.quality, self.restart_interval,
+                                                  self.out.data_ptr(), self.capacity, self.size.data_ptr(), self.workspace.data_ptr(),
+                                                  self.workspace.numel(), _stream_ptr(self.device)), "d2s_jpeg_encode")
+        return self.out, self.size
+
+    def encode_bytes(self, rgb_hwc: torch.Tensor) -> bytes:
+        out, size = self.encode(rgb_hwc)
+        n = int(size.item())
+        if n == 0:
+            raise RuntimeError(f"JpegEncoder: the stream did not fit the {self.capacity}-byte buffer")
+        return out[:n].cpu().numpy().tobytes()
+
+
 def make_sbs_dibr(rgb: torch.Tensor, depth: torch.Tensor, ipd_uv=0.064, depth_ratio=1.0, convergence=0.0, display_mode="Half-SBS", *,
                   roll=0.0, resolution=None, search_radius=12, depth_tolerance=0.012, blur_radius=2.5, feather_enabled=False,
                   feather_width=0.0, corner_radius=0.0, rgb_layout="CHW", out: torch.Tensor | None = None, out_dtype=torch.float32,

@@ -182,6 +182,21 @@ int d2s_overlay_fps(const d2s_image *rgb, int h, int w, const char *text, d2s_st
  * the layout NVENC / nvJPEG take.  h, w even.  row_pitch_bytes <= 0: tightly packed (3 * w). */
 int d2s_rgb_to_nv12(const uint8_t *rgb_hwc, int64_t row_pitch_bytes, int h, int w, uint8_t *nv12, d2s_stream_t stream);
 
+/* Packed u8 HWC frame -> a complete baseline JPEG stream, encoded on the device: replaces cv2.imencode(".jpg", bgr,
+ * [IMWRITE_JPEG_QUALITY, quality]) in MJPEGStreamer._encoder_loop (reference streamer.py:250-256) AND make_sbs's float32
+ * device->host copy (depth.py:767-773); MJPEGStreamer's `encoded_frame` (streamer.py:254) is the wire boundary that remains.
+ * The stream is byte-identical to what cv2.imencode (OpenCV's libjpeg-turbo: JFIF, YCbCr 4:2:0, Annex K tables, islow DCT) writes
+ * for the same frame with IMWRITE_JPEG_RST_INTERVAL = restart_interval; restart markers (>= 1 MCU of 16x16 pixels per interval,
+ * required: the encoder is parallel over intervals) do not change decoded pixels.  h, w even.
+ *   jpeg / capacity   device buffer for the stream; d2s_jpeg_max_bytes() can never overflow, smaller is allowed
+ *   size_out          device uint32: stream length in bytes, or 0 if it did not fit `capacity`
+ *   workspace         device scratch of d2s_jpeg_workspace_bytes(h, w, restart_interval)
+ * Asynchronous on `stream`; never allocates. */
+size_t d2s_jpeg_workspace_bytes(int h, int w, int restart_interval);
+size_t d2s_jpeg_max_bytes(int h, int w, int restart_interval);
+int d2s_jpeg_encode(const uint8_t *rgb_hwc, int64_t row_pitch_bytes, int h, int w, int quality, int restart_interval, uint8_t *jpeg,
+                    size_t capacity, uint32_t *size_out, void *workspace, size_t workspace_bytes, d2s_stream_t stream);
+
 /* ---- occlusion-aware stereo rendering ----
  * The reference's OpenGL viewer warps with a fragment shader that handles disocclusions (reference viewer.py:386-631:
  * 3-tap depth smoothing, depth shaping, edge falloff, 2-tap disocclusion confidence :421-435, push-pull inpaint :437-506, border
@@ -221,6 +236,15 @@ int d2s_make_sbs_dibr(const d2s_dibr_params *p, d2s_stream_t stream);
  * same frame (same kernels).  The DepthStabilizer EMA (depth.py:1865-1887) orders consecutive frames with an event between the
  * two graphs of a frame; submit frames of one video in order.  One caller thread per pipe. */
 typedef struct d2s_pipe *d2s_pipe_handle;
+enum d2s_out_format { D2S_OUT_PACKED = 0, D2S_OUT_NV12 = 1, D2S_OUT_JPEG = 2 };
+/* D2S_OUT_JPEG result of one stream, at stride `out_bytes` (d2s_pipe_geometry) in the slot's output buffer.  With host_io the pipe
+ * copies only as many bytes as recent frames needed (a frame that outgrows the estimate costs one extra copy inside d2s_pipe_wait);
+ * d2s_pipe_wait fails with D2S_ERR_INVALID if a stream did not fit out_bytes (oh * ow * 3 / 2, the NV12 size). */
+typedef struct d2s_pipe_jpeg_frame {
+    uint32_t size;          /* bytes of `data` that hold the stream (SOI ... EOI) */
+    uint32_t reserved[3];
+    uint8_t data[1];
+} d2s_pipe_jpeg_frame;
 typedef struct d2s_pipe_config {
     int32_t frame_h, frame_w, channels; /* captured frame: u8 HWC, BGRA (4) or BGR (3) (depth.py:549) */
     int32_t target_height;        /* process(img, target_height): bilinear-antialias downscale when < frame_h (depth.py:555-566) */
@@ -237,12 +261,17 @@ typedef struct d2s_pipe_config {
     double ipd_uv, depth_ratio, convergence;   /* make_sbs (depth.py:2186) */
     int32_t display_mode, fill_16_9;
     int32_t out_dtype;            /* packed frame [oh, ow, 3] HWC: D2S_F32 = what make_sbs returns (depth.py:2231), D2S_U8, D2S_F16 */
-    int32_t out_nv12;             /* 1 (needs out_dtype U8, even oh / ow): the result is the NV12 frame [oh * 3 / 2, ow] u8 (d2s_rgb_to_nv12) */
+    int32_t out_format;           /* what the caller receives per stream.  D2S_OUT_PACKED (0): the packed frame [oh, ow, 3] of out_dtype;
+                                     D2S_OUT_NV12 (1; needs out_dtype U8, even oh / ow): [oh * 3 / 2, ow] u8 (d2s_rgb_to_nv12);
+                                     D2S_OUT_JPEG (2; same needs): a d2s_pipe_jpeg_frame — the complete JPEG stream d2s_jpeg_encode
+                                     writes for the packed frame (byte-identical to cv2.imencode, streamer.py:250-256) */
     int32_t slots;                /* frames in flight (1..64); > 1 builds throughput-policy plans */
     int32_t host_io;              /* 1: frames come from and results go to pinned HOST memory (H2D / D2H copies on the slot's stream) */
     int32_t streams;              /* concurrent video streams sharing the pipe (0/1: one).  One submit takes ONE frame of EVERY stream:
                                      `frame` is [streams][frame_h, frame_w, channels], the result [streams][oh, ow, 3]; the network runs
                                      them as one batch (BASELINE configs 3/5: 8 x 4K), each stream keeps its own DepthStabilizer state */
+    int32_t jpeg_quality;         /* D2S_OUT_JPEG: IMWRITE_JPEG_QUALITY (MJPEGStreamer's `quality`, streamer.py:113); 0 -> 90 */
+    int32_t jpeg_restart_interval;/* D2S_OUT_JPEG: MCUs (16x16 pixels) per restart interval; 0 -> 2 */
     int32_t reserved[1];
 } d2s_pipe_config;
 /* Host-synchronous (allocates the slots, builds their plans, captures their graphs).  The pipe borrows `engine`: destroy the pipe

@@ -18,7 +18,7 @@ def build(force: bool = False) -> str:
     """Compile the C restatements with gcc (strict fp32: -ffp-contract=off). Returns the .so path."""
     os.makedirs(BUILD_DIR, exist_ok=True)
     so = os.path.join(BUILD_DIR, "libd2s_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("warp_oracle.c", "dibr_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("warp_oracle.c", "dibr_oracle.c", "jpeg_oracle.c")]
     if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", so, *srcs, "-lm"]
