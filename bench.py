@@ -348,7 +348,7 @@ def pipe_legs(B, depth, frames_dev, frames_host, h, w, streams, slots, steps, ou
             mean = float(np.mean(sizes))
             d2h = int(fpp * ((int(mean * 1.25) + 16 + 65535) // 65536) * 65536)
             extra = {"jpeg_bytes_per_frame": mean, "jpeg_bytes_per_pixel": mean / (h * 2 * w), "content": "desktop-like" if name.endswith("_desktop") else "uniform noise",
-                     "jpeg": "quality 90, restart interval 2 MCUs; byte-identical to cv2.imencode (tests/test_jpeg_gpu.py)"}
+                     "jpeg": "quality 90, restart interval 4 MCUs; byte-identical to cv2.imencode (tests/test_jpeg_gpu.py)"}
         else:
             d2h = fpp * h * 2 * w * 3 * es if fmt == "rgb" else fpp * h * 2 * w * 3 // 2
         fps = B.world * steps * fpp / (t["ms"] / 1e3)

@@ -12,8 +12,9 @@
 //               1,2,1,2) into shared memory with libjpeg's edge rules (right edge replicated at full resolution, bottom edge
 //               replicated after downsampling), then 8 threads per 8x8 block run jfdctint.c's row and column passes and
 //               jcdctmgr.c's round-half-away quantisation; coefficients leave in zig-zag order, one coalesced 16-byte store a thread.
-//   entropy     one thread per restart interval: jchuff.c's encode_one_block over the interval's MCUs into a private slot sized
-//               for the worst case (so it cannot overflow), 0xFF stuffing and the 1-bit padding included; writes the slot's length.
+//   entropy     one warp per restart interval, the 64 coefficients of a block coded side by side (ballot -> zero runs -> codewords ->
+//               warp scan -> OR into a shared-memory bit buffer): jchuff.c's encode_one_block, 0xFF stuffing and the 1-bit padding
+//               included, into a private slot sized for the worst case (so it cannot overflow); writes the slot's length.
 //   scan        exclusive prefix sum of (length + 2 marker bytes) over the intervals: one CTA.
 //   gather      one warp per interval copies its slot behind the header and appends RSTn (or EOI after the last); writes the size.
 // Luma blocks past the component's own block grid (1080 rows = 135 block rows, but 68 MCU rows hold 136) are libjpeg's "dummy
@@ -28,7 +29,7 @@ constexpr int JG = 8;                 // MCUs per CTA of the transform kernel
 constexpr int JT = JG * 6 * 8;        // 8 threads per 8x8 block
 constexpr int kBlockWorstBytes = 416; // 20 + 63 * 26 bits, every byte stuffed
 
-struct JpegQuant { uint16_t div[2][64]; uint8_t izz[64]; };     // 8 * quantval in natural order; natural index -> zig-zag position
+struct JpegQuant { uint16_t div[2][64]; uint32_t rcp[2][64]; uint8_t izz[64]; };   // 8 * quantval (natural order), floor(2^32 / div) + 1, natural index -> zig-zag position
 struct JpegHuff { uint32_t dc[2][16]; uint32_t ac[2][256]; };   // code << 5 | size
 struct JpegHeader { uint8_t bytes[640]; int len; };
 
@@ -94,7 +95,10 @@ static void build_tables(int h, int w, int quality, int restart_interval, JpegQu
         }
     zigzag_positions(jq.izz);
     for (int t = 0; t < 2; ++t)
-        for (int n = 0; n < 64; ++n) jq.div[t][n] = (uint16_t)(qz[t][jq.izz[n]] << 3);
+        for (int n = 0; n < 64; ++n) {
+            jq.div[t][n] = (uint16_t)(qz[t][jq.izz[n]] << 3);
+            jq.rcp[t][n] = (uint32_t)((1ull << 32) / jq.div[t][n]) + 1u;   // a / div == umulhi(a, rcp) while a * div < 2^32 (here a < 2^17, div < 2^11)
+        }
     derive_huffman(kBits[0], kDcVals, jh.dc[0], 16);
     derive_huffman(kBits[2], kDcVals, jh.dc[1], 16);
     derive_huffman(kBits[1], kAcLuma, jh.ac[0], 256);
@@ -154,6 +158,11 @@ __global__ void __launch_bounds__(JT) jpeg_transform_kernel(const uint8_t *__res
     __shared__ int16_t sC[2][8][JG * 8 + 2];
     __shared__ int sW[JG * 6][8][9];
     __shared__ __align__(16) int16_t sO[JG * 6][64];
+    __shared__ uint32_t sRcp[2][64];                                  // (lanes index these by their own column: not for the constant bank)
+    __shared__ uint16_t sDiv[2][64];
+    __shared__ uint8_t sIzz[64];
+    if (threadIdx.x < 128) { sRcp[threadIdx.x >> 6][threadIdx.x & 63] = q.rcp[threadIdx.x >> 6][threadIdx.x & 63]; sDiv[threadIdx.x >> 6][threadIdx.x & 63] = q.div[threadIdx.x >> 6][threadIdx.x & 63]; }
+    else if (threadIdx.x < 192) sIzz[threadIdx.x - 128] = q.izz[threadIdx.x - 128];
     const int my = blockIdx.y, mx0 = blockIdx.x * JG;
     const bool pairs_ok = ((pitch & 1) == 0) && ((((uintptr_t)rgb) & 1) == 0);
 
@@ -213,10 +222,9 @@ __global__ void __launch_bounds__(JT) jpeg_transform_kernel(const uint8_t *__res
     const int tb = b6 < 4 ? 0 : 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {                                     // jcdctmgr.c quantize: round half away from zero
-        const int nat = i * 8 + r, qv = q.div[tb][nat];
-        const int a = abs(d[i]) + (qv >> 1);
-        const int v = a >= qv ? a / qv : 0;
-        sO[blk][q.izz[nat]] = (int16_t)(d[i] < 0 ? -v : v);
+        const int nat = i * 8 + r, qv = sDiv[tb][nat];
+        const int v = (int)__umulhi((uint32_t)(abs(d[i]) + (qv >> 1)), sRcp[tb][nat]);
+        sO[blk][sIzz[nat]] = (int16_t)(d[i] < 0 ? -v : v);
     }
     __syncthreads();
     const int valid = min(JG, mcus_x - mx0) * 6 * 8;                  // 16-byte pieces of this CTA's MCUs
@@ -225,112 +233,141 @@ __global__ void __launch_bounds__(JT) jpeg_transform_kernel(const uint8_t *__res
 }
 
 // ---------------------------------------------------------------------------------------------------------------- entropy coding
-// Bytes leave through a 32-bit staging word (slots are 4-byte aligned), so a thread issues one store per four stream bytes.
-struct BitWriter {
-    uint32_t *wp;          // next word of the slot
-    uint32_t stage;        // bytes of the current word, little-endian
-    uint32_t pos;          // bytes written so far
-    uint64_t acc;
-    int nbits;
-    __device__ __forceinline__ void byte(uint32_t v) {
-        stage |= v << ((pos & 3u) * 8u);
-        if ((++pos & 3u) == 0u) { *wp++ = stage; stage = 0u; }
-    }
-    __device__ __forceinline__ void put(uint32_t bits, int size) {    // `bits` already masked to `size` bits
-        acc = (acc << size) | bits;
-        nbits += size;
-        while (nbits >= 8) {
-            const uint32_t v = (uint32_t)(acc >> (nbits - 8)) & 0xFFu;
-            byte(v);
-            if (v == 0xFFu) byte(0u);
-            nbits -= 8;
+// One WARP = one restart interval; the 64 coefficients of a block are coded side by side.  Lane l owns zig-zag positions l and
+// l + 32: two ballots give the block's non-zero mask, from which every lane reads off the zero run in front of its coefficients
+// (jchuff.c encode_one_block's run/size symbols, ZRLs in front when the run is 16+) and builds its <= 26-bit codeword; lane 0's first item is the DC
+// difference, lane 31's second item is the EOB when position 63 is zero.  A warp scan of the lengths places the codewords, which
+// are OR-ed into a big-endian bit buffer in shared memory; when the buffer might not hold another MCU (and at the end) the completed
+// bytes go to the interval's slot with 0xFF stuffing (ballot + popc for the positions) and the last partial byte is carried over.
+constexpr int EW = 8;                     // warps (restart intervals) per CTA
+constexpr int kMcuBits = 6 * 1658;        // worst case of one MCU
+constexpr int kBitWords = 640;            // bit buffer per warp: flushed when the next MCU might not fit (typically once per interval)
+
+// OR `n` bits (right-aligned in v) into the buffer at bit offset o; stream bit i lives in word i / 32 at bit 31 - i % 32
+__device__ __forceinline__ void put_item(uint32_t *buf, int o, uint32_t v, int n) {          // n <= 32: at most two words
+    const uint32_t hi = v << (32 - n);
+    const int w = o >> 5, s = o & 31;
+    const uint32_t x0 = hi >> s, x1 = s ? hi << (32 - s) : 0u;
+    if (x0) atomicOr(&buf[w], x0);
+    if (x1) atomicOr(&buf[w + 1], x1);
+}
+
+// one AC coefficient t at zig-zag position k: v/n = Huffman code of (run % 16, size) followed by the value bits (<= 26 bits);
+// nz = number of ZRL symbols (16 zeros each) that go in front of it
+__device__ __forceinline__ void ac_item(int t, int k, unsigned long long mask, const uint32_t *ac, uint32_t &v, int &n, int &nz) {
+    const unsigned long long below = mask & ((1ull << k) - 1ull);
+    const int prev = below ? 63 - __clzll((long long)below) : 0;      // position 0 is the DC term
+    const int run = k - 1 - prev;
+    nz = run >> 4;
+    const int nb = 32 - __clz(abs(t));
+    const uint32_t sym = ac[((run & 15) << 4) | nb];
+    v = ((sym >> 5) << nb) | ((uint32_t)(t < 0 ? t - 1 : t) & ((1u << nb) - 1u));
+    n = (int)(sym & 31u) + nb;
+}
+
+__device__ __forceinline__ void put_ac(uint32_t *buf, int o, uint32_t v, int n, int nz, uint32_t zrl) {
+    for (int i = 0; i < nz; ++i) { put_item(buf, o, zrl >> 5, (int)(zrl & 31u)); o += (int)(zrl & 31u); }   // rare: runs of 16+ zeros
+    put_item(buf, o, v, n);
+}
+
+// completed bytes -> slot (with stuffing); the partial byte moves to the front of the cleared buffer
+__device__ __forceinline__ void flush_bytes(uint32_t *buf, int &bitpos, uint8_t *out, uint32_t &outpos, int lane) {
+    __syncwarp();
+    const int nB = bitpos >> 3;
+    uint32_t ffs = 0;
+    for (int j0 = 0; j0 < nB; j0 += 32) {
+        const int j = j0 + lane;
+        const bool valid = j < nB;
+        const uint32_t b = valid ? (buf[j >> 2] >> (24 - 8 * (j & 3))) & 0xFFu : 0u;
+        const uint32_t ffm = __ballot_sync(0xffffffffu, valid && b == 0xFFu);
+        if (valid) {
+            const uint32_t p = outpos + (uint32_t)j + ffs + (uint32_t)__popc(ffm & ((1u << lane) - 1u));
+            out[p] = (uint8_t)b;
+            if (b == 0xFFu) out[p + 1] = 0;
         }
+        ffs += (uint32_t)__popc(ffm);
     }
-    __device__ __forceinline__ uint32_t finish() {                    // pad with 1 bits (jchuff.c flush_bits), write the last partial word
-        if (nbits) put((1u << (8 - nbits)) - 1u, 8 - nbits);
-        if (pos & 3u) *wp = stage;
-        return pos;
-    }
-};
-
-__device__ __forceinline__ void put_value(BitWriter &bw, uint32_t sym, int t, int nb) {               // Huffman code, then the value bits
-    const int t2 = t < 0 ? t - 1 : t;
-    bw.put(((sym >> 5) << nb) | ((uint32_t)t2 & ((1u << nb) - 1u)), (int)(sym & 31u) + nb);
+    outpos += (uint32_t)nB + ffs;
+    const uint32_t carry = (bitpos & 7) ? (buf[nB >> 2] >> (24 - 8 * (nB & 3))) & 0xFFu : 0u;
+    __syncwarp();
+    for (int i = lane; i <= (bitpos >> 5) + 2 && i < kBitWords; i += 32) buf[i] = 0u;
+    __syncwarp();
+    if (lane == 0 && carry) buf[0] = carry << 24;
+    bitpos &= 7;
+    __syncwarp();
 }
 
-// four zig-zag coefficients packed in 64 bits: jump from non-zero to non-zero (jchuff.c encode_one_block's run/size loop)
-__device__ __forceinline__ void code_four(BitWriter &bw, const uint32_t *s_ac, unsigned long long x, int &run) {
-    int left = 4;
-    while (x) {
-        const int hz = (__ffsll((long long)x) - 1) >> 4;
-        run += hz;
-        const int t = (int)(int16_t)((x >> (16 * hz)) & 0xFFFFull);
-        x = hz == 3 ? 0ull : x >> (16 * (hz + 1));
-        left -= hz + 1;
-        while (run > 15) { const uint32_t z = s_ac[0xF0]; bw.put(z >> 5, (int)(z & 31u)); run -= 16; }
-        const int nb = 32 - __clz(abs(t));
-        put_value(bw, s_ac[(run << 4) + nb], t, nb);
-        run = 0;
-    }
-    run += left;
-}
-
-__device__ __forceinline__ void load_block(uint4 (&v)[8], const int16_t *coef, size_t block) {
-    const uint4 *cp = (const uint4 *)(coef + block * 64);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = __ldg(cp + c);
-}
-
-// One thread = one restart interval.  The thread's chain of dependent loads is what bounds it, so the 128 bytes of block b+1 are
-// requested before block b is coded.
-__global__ void __launch_bounds__(128) jpeg_entropy_kernel(const int16_t *__restrict__ coef, int n_mcus, int mcus_x, int yblk_w, int yblk_h,
-                                                           int ri, int n_int, const __grid_constant__ JpegHuff hf,
-                                                           uint8_t *__restrict__ slots, int slot_bytes, uint32_t *__restrict__ lens) {
+__global__ void __launch_bounds__(EW * 32) jpeg_entropy_kernel(const int16_t *__restrict__ coef, int n_mcus, int mcus_x, int yblk_w, int yblk_h,
+                                                               int ri, int n_int, const __grid_constant__ JpegHuff hf,
+                                                               uint8_t *__restrict__ slots, int slot_bytes, uint32_t *__restrict__ lens) {
     __shared__ uint32_t s_ac[2][256], s_dc[2][16];
-    for (int i = threadIdx.x; i < 512; i += 128) s_ac[i >> 8][i & 255] = hf.ac[i >> 8][i & 255];
+    __shared__ uint32_t s_bits[EW][kBitWords];
+    for (int i = threadIdx.x; i < 512; i += EW * 32) s_ac[i >> 8][i & 255] = hf.ac[i >> 8][i & 255];
     if (threadIdx.x < 32) s_dc[threadIdx.x >> 4][threadIdx.x & 15] = hf.dc[threadIdx.x >> 4][threadIdx.x & 15];
+    for (int i = threadIdx.x; i < EW * kBitWords; i += EW * 32) (&s_bits[0][0])[i] = 0u;
     __syncthreads();
-    const int it = blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, it = blockIdx.x * EW + wid;
     if (it >= n_int) return;
-    BitWriter bw{(uint32_t *)(slots + (size_t)it * slot_bytes), 0u, 0u, 0ull, 0};
-    int last_y = 0, last_cb = 0, last_cr = 0;
+    uint32_t *buf = s_bits[wid];
+    uint8_t *out = slots + (size_t)it * slot_bytes;
+    uint32_t outpos = 0;
+    int bitpos = 0, last_y = 0, last_cb = 0, last_cr = 0;
     const int m0 = it * ri, m_end = min(n_mcus, m0 + ri);
-    const size_t blk_end = (size_t)m_end * 6;
-    uint4 cur[8], nxt[8];
-    load_block(nxt, coef, (size_t)m0 * 6);
+    const int16_t *cp = coef + (size_t)m0 * 6 * 64;
+    int nx0 = __ldg(cp + lane), nx1 = __ldg(cp + lane + 32);          // the next block's coefficients are always in flight
     for (int m = m0; m < m_end; ++m) {
         const int my = m / mcus_x, mx = m - my * mcus_x;
         int prev_dc = 0;
 #pragma unroll 1
         for (int b = 0; b < 6; ++b) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
-            const size_t nb_idx = (size_t)m * 6 + b + 1;
-            if (nb_idx < blk_end) load_block(nxt, coef, nb_idx);
+            int c0 = nx0, c1 = nx1;
+            cp += 64;
+            if (b < 5 || m + 1 < m_end) { nx0 = __ldg(cp + lane); nx1 = __ldg(cp + lane + 32); }
             const int tb = b < 4 ? 0 : 1;
             const bool dummy = b < 4 && (2 * my + (b >> 1) >= yblk_h || 2 * mx + (b & 1) >= yblk_w);   // jccoefct.c
-            const int dc = dummy ? prev_dc : (int)(int16_t)(cur[0].x & 0xFFFFu);
+            if (dummy) { c0 = 0; c1 = 0; }
+            int dc = __shfl_sync(0xffffffffu, c0, 0);
+            if (dummy) dc = prev_dc;
             prev_dc = dc;
             int diff;
             if (b < 4) { diff = dc - last_y; last_y = dc; } else if (b == 4) { diff = dc - last_cb; last_cb = dc; } else { diff = dc - last_cr; last_cr = dc; }
+            const uint32_t mlo = __ballot_sync(0xffffffffu, c0 != 0 && lane != 0), mhi = __ballot_sync(0xffffffffu, c1 != 0);
+            const unsigned long long mask = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
             const int nbd = 32 - __clz(abs(diff));
             const uint32_t symd = s_dc[tb][nbd];
-            if (nbd) put_value(bw, symd, diff, nbd); else bw.put(symd >> 5, (int)(symd & 31u));
-            int run = -1;                                             // the DC slot is masked to zero below and must not count
-            if (!dummy) {
-                cur[0].x &= 0xFFFF0000u;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    code_four(bw, s_ac[tb], (unsigned long long)cur[c].x | ((unsigned long long)cur[c].y << 32), run);
-                    code_four(bw, s_ac[tb], (unsigned long long)cur[c].z | ((unsigned long long)cur[c].w << 32), run);
-                }
-            } else {
-                run = 63;
+            const uint32_t vd = ((symd >> 5) << nbd) | ((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << nbd) - 1u));
+            const int nd = (int)(symd & 31u) + nbd;                   // <= 20 bits
+            const uint32_t eob = s_ac[tb][0], zrl = s_ac[tb][0xF0];
+            if (mask == 0ull) {                                       // no AC term at all (flat areas): DC difference + EOB, one store
+                if (lane == 0) put_item(buf, bitpos, (vd << (eob & 31u)) | (eob >> 5), nd + (int)(eob & 31u));
+                bitpos += nd + (int)(eob & 31u);
+                continue;
             }
-            if (run > 0) { const uint32_t e = s_ac[tb][0]; bw.put(e >> 5, (int)(e & 31u)); }
+            uint32_t v0 = 0, v1 = 0;
+            int n0 = 0, n1 = 0, z0 = 0, z1 = 0;
+            if (lane == 0) { v0 = vd; n0 = nd; }
+            else if (c0 != 0) ac_item(c0, lane, mask, s_ac[tb], v0, n0, z0);
+            if (c1 != 0) ac_item(c1, lane + 32, mask, s_ac[tb], v1, n1, z1);
+            else if (lane == 31) { v1 = eob >> 5; n1 = (int)(eob & 31u); }   // position 63 is zero: EOB
+            const int l0 = n0 + z0 * (int)(zrl & 31u), l1 = n1 + z1 * (int)(zrl & 31u);
+            uint32_t incl = (uint32_t)l0 | ((uint32_t)l1 << 16);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (n0) put_ac(buf, bitpos + (int)(incl & 0xFFFFu) - l0, v0, n0, z0, zrl);
+            if (n1) put_ac(buf, bitpos + (int)(tot & 0xFFFFu) + (int)(incl >> 16) - l1, v1, n1, z1, zrl);
+            bitpos += (int)(tot & 0xFFFFu) + (int)(tot >> 16);
         }
+        if (bitpos + kMcuBits > (kBitWords - 3) * 32) flush_bytes(buf, bitpos, out, outpos, lane);
     }
-    lens[it] = bw.finish();
+    flush_bytes(buf, bitpos, out, outpos, lane);
+    if (bitpos & 7) {                                                 // jchuff.c flush_bits: pad the last byte with 1 bits
+        const int pad = 8 - (bitpos & 7);
+        if (lane == 0) put_item(buf, bitpos, (1u << pad) - 1u, pad);
+        bitpos += pad;
+        flush_bytes(buf, bitpos, out, outpos, lane);
+    }
+    if (lane == 0) lens[it] = outpos;
 }
 
 // exclusive scan of (len + 2) over the intervals; offs[n] = total stream length including the header
@@ -338,7 +375,13 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(const uint32_t *__restr
     __shared__ uint32_t warp_sum[32];
     const int chunk = (n + 1023) / 1024, lo = min(n, (int)threadIdx.x * chunk), hi = min(n, lo + chunk);
     uint32_t mine = 0;
-    for (int i = lo; i < hi; ++i) mine += lens[i] + 2u;
+    for (int i = lo; i < hi; i += 8) {                                // independent loads, eight at a time
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i + k < hi ? lens[i + k] + 2u : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += v[k];
+    }
     uint32_t incl = mine;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -353,7 +396,13 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(const uint32_t *__restr
     }
     __syncthreads();
     uint32_t base = header_len + (wid ? warp_sum[wid - 1] : 0u) + incl - mine;
-    for (int i = lo; i < hi; ++i) { offs[i] = base; base += lens[i] + 2u; }
+    for (int i = lo; i < hi; i += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i + k < hi ? lens[i + k] + 2u : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (i + k < hi) offs[i + k] = base; base += v[k]; }
+    }
     if (threadIdx.x == 1023) offs[n] = base;
 }
 
@@ -424,7 +473,7 @@ int jpeg_encode_launch(const uint8_t *rgb, long long pitch, int h, int w, int qu
     uint32_t *lens = (uint32_t *)(ws + g.lens_off), *offs = (uint32_t *)(ws + g.offs_off);
     D2S_REQUIRE(g.mcus_y <= 65535, "d2s_jpeg_encode: frame height %d", h);
     D2S_LAUNCH(jpeg_transform_kernel, dim3(ceil_div(g.mcus_x, JG), g.mcus_y), JT, 0, stream, rgb, pitch, h, w, g.mcus_x, jq, coef);
-    D2S_LAUNCH(jpeg_entropy_kernel, ceil_div(g.n_int, 128), 128, 0, stream, (const int16_t *)coef, g.n_mcus, g.mcus_x, ceil_div(w, 8), ceil_div(h, 8), ri,
+    D2S_LAUNCH(jpeg_entropy_kernel, ceil_div(g.n_int, EW), EW * 32, 0, stream, (const int16_t *)coef, g.n_mcus, g.mcus_x, ceil_div(w, 8), ceil_div(h, 8), ri,
                g.n_int, jh, slots, g.slot_bytes, lens);
     D2S_LAUNCH(jpeg_scan_kernel, 1, 1024, 0, stream, (const uint32_t *)lens, g.n_int, (uint32_t)hd.len, offs);
     D2S_LAUNCH(jpeg_gather_kernel, ceil_div(g.n_int, 8), 256, 0, stream, (const uint8_t *)slots, g.slot_bytes, (const uint32_t *)lens, (const uint32_t *)offs,

@@ -61,7 +61,7 @@ struct d2s_pipe {
     size_t frame_bytes, out_bytes, res_bytes, rgb_es, out_es;   // out: the packed RGB frame, res: what the caller receives (per stream)
     size_t ws_proc_bytes, ws_pre_bytes, ws_post_bytes;
     size_t ws_jpeg_bytes = 0, jpeg_head = 0;  // D2S_OUT_JPEG: workspace per stream; bytes per stream the next submit copies to the host
-    int jpeg_quality = 90, jpeg_ri = 2;
+    int jpeg_quality = 90, jpeg_ri = 4;
     void *ema_state = nullptr;               // [Hm,Wm] fp16, NaN = unset (d2s_post_params.ema_valid == 2)
     cudaEvent_t last_ema = nullptr;          // EMA event of the most recently submitted frame
     bool trace = false;
@@ -279,7 +279,7 @@ extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2
     }
     if (cfg->out_format == D2S_OUT_JPEG) {
         p->jpeg_quality = cfg->jpeg_quality > 0 ? cfg->jpeg_quality : 90;
-        p->jpeg_ri = cfg->jpeg_restart_interval > 0 ? cfg->jpeg_restart_interval : 2;
+        p->jpeg_ri = cfg->jpeg_restart_interval > 0 ? cfg->jpeg_restart_interval : 4;
         p->res_bytes = (p->res_bytes + offsetof(d2s_pipe_jpeg_frame, data) + 1024 + 255) & ~(size_t)255;
         if (d2s_jpeg_workspace_bytes(p->oh, p->ow, p->jpeg_ri) == 0) { delete p; return D2S_ERR_INVALID; }
         p->ws_jpeg_bytes = (jpeg_workspace(p->oh, p->ow, p->jpeg_ri) + 255) & ~(size_t)255;

@@ -115,7 +115,7 @@ def _jpeg_streams(buf, streams):
 class StereoPipeline:
     def __init__(self, depth_slots: int = 3, display_mode="Full-SBS", ipd_uv=0.064, depth_ratio=2.0, convergence=0.0,
                  fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None, streams=1,
-                 out_format="rgb", jpeg_quality=90, jpeg_restart_interval=2):
+                 out_format="rgb", jpeg_quality=90, jpeg_restart_interval=4):
         """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and the post-process settings live there).
         A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224).
         streams > 1: that many concurrent video streams share the pipeline; every submit takes one frame of each, stacked as

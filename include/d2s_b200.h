@@ -271,7 +271,7 @@ typedef struct d2s_pipe_config {
                                      `frame` is [streams][frame_h, frame_w, channels], the result [streams][oh, ow, 3]; the network runs
                                      them as one batch (BASELINE configs 3/5: 8 x 4K), each stream keeps its own DepthStabilizer state */
     int32_t jpeg_quality;         /* D2S_OUT_JPEG: IMWRITE_JPEG_QUALITY (MJPEGStreamer's `quality`, streamer.py:113); 0 -> 90 */
-    int32_t jpeg_restart_interval;/* D2S_OUT_JPEG: MCUs (16x16 pixels) per restart interval; 0 -> 2 */
+    int32_t jpeg_restart_interval;/* D2S_OUT_JPEG: MCUs (16x16 pixels) per restart interval; 0 -> 4 */
     int32_t reserved[1];
 } d2s_pipe_config;
 /* Host-synchronous (allocates the slots, builds their plans, captures their graphs).  The pipe borrows `engine`: destroy the pipe

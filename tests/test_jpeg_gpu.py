@@ -100,7 +100,7 @@ def test_pipeline_jpeg_output(cuda_device):
     p8 = StereoPipeline(depth_slots=2, display_mode="Half-SBS", out_dtype=torch.uint8, streams=2)
     pj = StereoPipeline(depth_slots=2, display_mode="Half-SBS", out_dtype=torch.uint8, streams=2, out_format="jpeg")
     pairs = [np.stack([frames[i], frames[i + 3]]) for i in range(3)]
-    want2 = [[oj.encode_cv2(r[b].copy(), 90, 2) for b in range(2)] for r in p8.run(iter(pairs))]
+    want2 = [[oj.encode_cv2(r[b].copy(), 90, 4) for b in range(2)] for r in p8.run(iter(pairs))]
     got2 = [[bytes(x) for x in r] for r in pj.run(iter(pairs))]
     p8.close(); pj.close()
     assert got2 == want2

@@ -1,5 +1,5 @@
 """Device JPEG encoder: per-kernel times on the BASELINE output sizes (CUDA events, graph-free), stream sizes, cv2 host time."""
-import sys, time
+import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
 from oracle import jpeg as oj
@@ -10,7 +10,7 @@ for (h, w, name) in [(1080, 3840, "1080p Full-SBS"), (2160, 7680, "4K Full-SBS")
     for content in ("desktop", "noise"):
         img = oj.desktop_like(h, w, 1) if content == "desktop" else np.random.default_rng(0).integers(0, 256, (h, w, 3), dtype=np.uint8)
         t = torch.from_numpy(img).to(dev)
-        for ri in (1, 2, 4, 8, 16):
+        for ri in [int(x) for x in os.environ.get("JPEG_RI", "1,2,4,8,16").split(",")]:
             enc = JpegEncoder(h, w, dev, quality=90, restart_interval=ri)
             for _ in range(3): enc.encode(t)
             torch.cuda.synchronize()
