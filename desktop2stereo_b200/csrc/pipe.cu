@@ -280,7 +280,7 @@ extern "C" int d2s_pipe_create(d2s_handle engine, const d2s_pipe_config *cfg, d2
     if (cfg->out_format == D2S_OUT_JPEG) {
         p->jpeg_quality = cfg->jpeg_quality > 0 ? cfg->jpeg_quality : 90;
         p->jpeg_ri = cfg->jpeg_restart_interval > 0 ? cfg->jpeg_restart_interval : 4;
-        p->res_bytes = (p->res_bytes + offsetof(d2s_pipe_jpeg_frame, data) + 1024 + 255) & ~(size_t)255;
+        p->res_bytes = ((size_t)p->oh * p->ow * 3 + offsetof(d2s_pipe_jpeg_frame, data) + 4096 + 255) & ~(size_t)255;   // the raw frame's size: above quality-100 noise (2 B/px)
         if (d2s_jpeg_workspace_bytes(p->oh, p->ow, p->jpeg_ri) == 0) { delete p; return D2S_ERR_INVALID; }
         p->ws_jpeg_bytes = (jpeg_workspace(p->oh, p->ow, p->jpeg_ri) + 255) & ~(size_t)255;
         p->jpeg_head = std::min(p->res_bytes, std::max((size_t)65536, ((size_t)p->oh * p->ow / 4 + 65535) & ~(size_t)65535));

@@ -239,7 +239,7 @@ typedef struct d2s_pipe *d2s_pipe_handle;
 enum d2s_out_format { D2S_OUT_PACKED = 0, D2S_OUT_NV12 = 1, D2S_OUT_JPEG = 2 };
 /* D2S_OUT_JPEG result of one stream, at stride `out_bytes` (d2s_pipe_geometry) in the slot's output buffer.  With host_io the pipe
  * copies only as many bytes as recent frames needed (a frame that outgrows the estimate costs one extra copy inside d2s_pipe_wait);
- * d2s_pipe_wait fails with D2S_ERR_INVALID if a stream did not fit out_bytes (oh * ow * 3 / 2, the NV12 size). */
+ * d2s_pipe_wait fails with D2S_ERR_INVALID if a stream did not fit out_bytes (oh * ow * 3 + 4 KB: above uniform noise at quality 100). */
 typedef struct d2s_pipe_jpeg_frame {
     uint32_t size;          /* bytes of `data` that hold the stream (SOI ... EOI) */
     uint32_t reserved[3];
