@@ -70,7 +70,7 @@ class PipeConfig(C.Structure):
                 ("ipd_uv", C.c_double), ("depth_ratio", C.c_double), ("convergence", C.c_double),
                 ("display_mode", C.c_int32), ("fill_16_9", C.c_int32), ("out_dtype", C.c_int32), ("out_format", C.c_int32),
                 ("slots", C.c_int32), ("host_io", C.c_int32), ("streams", C.c_int32),
-                ("jpeg_quality", C.c_int32), ("jpeg_restart_interval", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("jpeg_quality", C.c_int32), ("jpeg_restart_interval", C.c_int32), ("fps_overlay", C.c_int32)]
 
 
 # every symbol include/d2s_b200.h declares: name -> (restype, argtypes)
@@ -103,6 +103,7 @@ SYMBOLS = {
     "d2s_make_sbs_dibr": (C.c_int, [C.POINTER(DibrParams), C.c_void_p]),
     "d2s_pipe_create": (C.c_int, [C.c_void_p, C.POINTER(PipeConfig), C.POINTER(C.c_void_p)]),
     "d2s_pipe_destroy": (C.c_int, [C.c_void_p]),
+    "d2s_pipe_set_fps_text": (C.c_int, [C.c_void_p, C.c_char_p]),
     "d2s_pipe_geometry": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_size_t)] * 2),
     "d2s_pipe_slot_buffers": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 6),
     "d2s_pipe_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

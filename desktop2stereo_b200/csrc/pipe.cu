@@ -13,6 +13,8 @@
 // weight tables of both resizes are input-independent and are built once at creation (the per-call entry points rebuild them).
 // Arithmetic is that of d2s_process / d2s_preprocess / d2s_infer / d2s_postprocess / d2s_make_sbs — the same kernels, launched
 // through the same code — so a frame through the pipe equals the same frame through the five calls, bit for bit.
+#include <string.h>
+
 #include <algorithm>
 #include <cstddef>
 #include <vector>
@@ -62,6 +64,7 @@ struct d2s_pipe {
     size_t ws_proc_bytes, ws_pre_bytes, ws_post_bytes;
     size_t ws_jpeg_bytes = 0, jpeg_head = 0;  // D2S_OUT_JPEG: workspace per stream; bytes per stream the next submit copies to the host
     int jpeg_quality = 90, jpeg_ri = 4;
+    char fps_text[40] = {0};                 // cfg.fps_overlay: drawn onto the RGB frame between the two graphs
     void *ema_state = nullptr;               // [Hm,Wm] fp16, NaN = unset (d2s_post_params.ema_valid == 2)
     cudaEvent_t last_ema = nullptr;          // EMA event of the most recently submitted frame
     bool trace = false;
@@ -168,7 +171,7 @@ static int build_slot(d2s_pipe *p, PipeSlot &s) {
     }
     D2S_CHECK_CUDA(cudaStreamSynchronize(s.stream));
 
-    const bool split = c.use_temporal_smooth != 0;
+    const bool split = c.use_temporal_smooth != 0 || c.fps_overlay != 0;   // something happens between the network and the warp
     auto warp_and_pack = [&](int b, cudaStream_t st) -> int {      // stereo warp (+ the output encoder: NV12 stages, or the whole JPEG)
         d2s_warp_params wp; fill_warp(p, s, b, &wp);
         int r = d2s_make_sbs(&wp, st);
@@ -359,13 +362,21 @@ extern "C" int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d
     D2S_CHECK_CUDA(cudaGraphLaunch(s.gA, st));
     long long kernels = s.kernels_a;
     if (s.gB) {
-        if (p->last_ema && p->last_ema != s.ema_ev) D2S_CHECK_CUDA(cudaStreamWaitEvent(st, p->last_ema, 0));
+        if (c.use_temporal_smooth && p->last_ema && p->last_ema != s.ema_ev) D2S_CHECK_CUDA(cudaStreamWaitEvent(st, p->last_ema, 0));
         for (int b = 0; b < p->B; ++b) {
             d2s_post_params pp; fill_post(p, s, b, &pp);
             if ((rc = postprocess_phases(&pp, POST_PHASE_EMA, st))) return rc;
         }
-        D2S_CHECK_CUDA(cudaEventRecord(s.ema_ev, st));
-        p->last_ema = s.ema_ev;
+        if (c.use_temporal_smooth) {
+            D2S_CHECK_CUDA(cudaEventRecord(s.ema_ev, st));
+            p->last_ema = s.ema_ev;
+        }
+        if (p->fps_text[0])                                   // make_sbs(fps=...): overlay_fps on the frame the warp reads (depth.py:2226-2227)
+            for (int b = 0; b < p->B; ++b) {
+                d2s_image img{};
+                img.base = rgb_of(p, s, b); img.dtype = c.rgb_dtype; img.sc = (int64_t)p->h * p->w; img.sy = p->w; img.sx = 1;
+                if ((rc = d2s_overlay_fps(&img, p->h, p->w, p->fps_text, (d2s_stream_t)st))) return rc;
+            }
         if (s.traced) D2S_CHECK_CUDA(cudaEventRecord(s.t[2], st));
         D2S_CHECK_CUDA(cudaGraphLaunch(s.gB, st));
         kernels += s.kernels_b;
@@ -401,6 +412,15 @@ extern "C" int d2s_pipe_wait(d2s_pipe_handle p, int slot) {
         }
         p->jpeg_head = std::min(p->res_bytes, std::max((size_t)65536, (need + need / 4 + 65535) & ~(size_t)65535));
     }
+    return D2S_OK;
+}
+
+extern "C" int d2s_pipe_set_fps_text(d2s_pipe_handle p, const char *text) {
+    D2S_REQUIRE(p != nullptr, "d2s_pipe_set_fps_text: null pipe");
+    D2S_REQUIRE(p->cfg.fps_overlay, "d2s_pipe_set_fps_text: the pipe was created without fps_overlay");
+    D2S_REQUIRE(!text || strlen(text) <= 32, "d2s_pipe_set_fps_text: text longer than 32 characters");
+    memset(p->fps_text, 0, sizeof(p->fps_text));
+    if (text) strcpy(p->fps_text, text);
     return D2S_OK;
 }
 

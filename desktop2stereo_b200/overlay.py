@@ -18,6 +18,16 @@ def reset_cache():
     _FPS_MASK_CACHE.update(text=None, frame=0)
 
 
+def next_text(fps: float) -> bytes:
+    """One step of the reference's text cache (depth.py:2061-2072): counts the call, refreshes the text on the first call and on
+    every 10th; returns the text to draw (ASCII, <= 32 characters)."""
+    cache = _FPS_MASK_CACHE
+    cache["frame"] += 1
+    if cache["text"] is None or cache["frame"] % cache["interval"] == 0:
+        cache["text"] = f"FPS: {fps:.1f}"
+    return cache["text"].encode("ascii", "replace")[:32]
+
+
 def overlay_fps(rgb: torch.Tensor, fps: float, *, layout: str = "CHW", inplace: bool = False) -> torch.Tensor:
     """rgb [3,h,w] (or [h,w,3] with layout='HWC') on the GPU, any of f32/f16/bf16/u8.  Returns a new tensor like the
     reference does unless inplace=True (the pipeline owns its frame and skips the copy)."""
@@ -25,9 +35,7 @@ def overlay_fps(rgb: torch.Tensor, fps: float, *, layout: str = "CHW", inplace: 
     if not rgb.is_cuda:
         raise _lib.D2SError("overlay_fps: rgb must live on a CUDA device; there is no CPU path")
     cache = _FPS_MASK_CACHE
-    cache["frame"] += 1
-    if cache["text"] is None or cache["frame"] % cache["interval"] == 0:
-        cache["text"] = f"FPS: {fps:.1f}"
+    next_text(fps)
     out = rgb if inplace else rgb.clone()
     h, w = (out.shape[1:] if layout == "CHW" else out.shape[:2])
     img = image_view(out, layout)

@@ -56,6 +56,7 @@ class _Pipe:
         c.out_format = {"rgb": 0, "nv12": 1, "jpeg": 2}[owner.out_format]
         c.jpeg_quality, c.jpeg_restart_interval = int(owner.jpeg_quality), int(owner.jpeg_restart_interval)
         self.jpeg = owner.out_format == "jpeg"
+        c.fps_overlay = int(owner.show_fps)
         self.handle = C.c_void_p()
         self.engine = engine                 # the pipe borrows the engine's plans: keep it alive for as long as the pipe lives
         self.device, self.host_io, self.L = owner.device, host_io, L
@@ -115,7 +116,7 @@ def _jpeg_streams(buf, streams):
 class StereoPipeline:
     def __init__(self, depth_slots: int = 3, display_mode="Full-SBS", ipd_uv=0.064, depth_ratio=2.0, convergence=0.0,
                  fill_16_9=False, use_temporal_smooth=True, out_dtype=torch.float32, device=None, target_height=None, streams=1,
-                 out_format="rgb", jpeg_quality=90, jpeg_restart_interval=4):
+                 out_format="rgb", jpeg_quality=90, jpeg_restart_interval=4, show_fps=False):
         """`desktop2stereo_b200.depth.init(...)` must have been called (the engine and the post-process settings live there).
         A temporal (Video-Depth-Anything) engine needs depth_slots == 1: its frames are sequential (vda2_s.py:189-224).
         streams > 1: that many concurrent video streams share the pipeline; every submit takes one frame of each, stacked as
@@ -125,7 +126,9 @@ class StereoPipeline:
         out_format="jpeg" (with out_dtype=torch.uint8): results are complete JPEG streams (1-D u8 arrays; a list of them when
         streams > 1), byte-identical to cv2.imencode(".jpg", bgr, [IMWRITE_JPEG_QUALITY, jpeg_quality, IMWRITE_JPEG_RST_INTERVAL,
         jpeg_restart_interval]) of the u8 frame — MJPEGStreamer's whole encoder loop (streamer.py:231-256) on the device; what
-        crosses PCIe is the compressed stream."""
+        crosses PCIe is the compressed stream.
+        show_fps=True: submit*(…, fps=value) draws the reference's "FPS: xx.x" overlay onto the frame before the warp, with
+        make_sbs's semantics (depth.py:2226-2227; the text refreshes on every 10th call, overlay.py)."""
         d2s_depth._need_init()
         engine = d2s_depth.model_wraper.model
         if getattr(engine.cfg, "temporal", 0) and depth_slots != 1:
@@ -138,6 +141,7 @@ class StereoPipeline:
         if out_format not in ("rgb", "nv12", "jpeg") or (out_format != "rgb" and out_dtype != torch.uint8):
             raise ValueError("out_format is 'rgb', 'nv12' or 'jpeg' (nv12 and jpeg need out_dtype=torch.uint8)")
         self.out_format, self.jpeg_quality, self.jpeg_restart_interval = out_format, jpeg_quality, jpeg_restart_interval
+        self.show_fps = bool(show_fps)
         self.params = dict(ipd_uv=ipd_uv, depth_ratio=depth_ratio, convergence=convergence, fill_16_9=fill_16_9,
                            display_mode=display_mode)
         self.use_temporal_smooth, self.out_dtype, self.target_height = use_temporal_smooth, out_dtype, target_height
@@ -168,11 +172,16 @@ class StereoPipeline:
         self.next = (self.next + 1) % self.n_slots
         return i
 
-    def _submit(self, pipe: _Pipe, slot: int, ptr, ready_stream, keep=None):
+    def _submit(self, pipe: _Pipe, slot: int, ptr, ready_stream, keep=None, fps=None):
         L = pipe.L
         if (self.trace is not None) != getattr(pipe, "_tracing", False):
             pipe._tracing = self.trace is not None
             _lib.check(L.d2s_pipe_set_trace(pipe.handle, int(pipe._tracing)), "d2s_pipe_set_trace")
+        if self.show_fps:        # make_sbs(fps=...): fps None -> no overlay on this frame (depth.py:2226)
+            from .overlay import next_text
+            _lib.check(L.d2s_pipe_set_fps_text(pipe.handle, next_text(fps) if fps is not None else None), "d2s_pipe_set_fps_text")
+        elif fps is not None:
+            raise ValueError("fps= needs StereoPipeline(show_fps=True)")
         with torch.cuda.device(self.device):
             _lib.check(L.d2s_pipe_submit(pipe.handle, slot, ptr, ready_stream), "d2s_pipe_submit")
         self._busy[slot] = pipe
@@ -181,7 +190,7 @@ class StereoPipeline:
         return t
 
     # ---- submission ----
-    def submit(self, frame_bgra: np.ndarray):
+    def submit(self, frame_bgra: np.ndarray, fps=None):
         """Host frame (BGRA/BGR u8 HWC ndarray) -> ticket.  Copies the frame into the slot's pinned buffer (the capture ->
         staging memcpy), then enqueues H2D + process + predict_depth + make_sbs + D2H on the slot's stream; returns immediately."""
         if frame_bgra.dtype != np.uint8:
@@ -189,18 +198,18 @@ class StereoPipeline:
         pipe = self._pipe(frame_bgra.shape, True)
         slot = self._acquire()
         np.copyto(pipe.host_in[slot], frame_bgra)
-        return self._submit(pipe, slot, None, None)
+        return self._submit(pipe, slot, None, None, fps=fps)
 
-    def submit_pinned(self, frame_pinned: torch.Tensor):
+    def submit_pinned(self, frame_pinned: torch.Tensor, fps=None):
         """Same, for a frame that already sits in pinned host memory (no host-side copy).  The tensor must stay alive and
         unchanged until the frame's result has been collected."""
         if not frame_pinned.is_pinned() or frame_pinned.dtype != torch.uint8 or not frame_pinned.is_contiguous():
             raise ValueError("submit_pinned needs a contiguous uint8 tensor in pinned host memory")
         pipe = self._pipe(frame_pinned.shape, True)
         slot = self._acquire()
-        return self._submit(pipe, slot, frame_pinned.data_ptr(), None, keep=frame_pinned)
+        return self._submit(pipe, slot, frame_pinned.data_ptr(), None, keep=frame_pinned, fps=fps)
 
-    def submit_device(self, frame_dev: torch.Tensor):
+    def submit_device(self, frame_dev: torch.Tensor, fps=None):
         """Frame already resident in HBM (produced on torch's current stream); the result stays on the device."""
         if not frame_dev.is_cuda or frame_dev.dtype != torch.uint8 or not frame_dev.is_contiguous():
             raise _lib.D2SError("submit_device needs a contiguous uint8 CUDA tensor (there is no CPU path)")
@@ -210,7 +219,7 @@ class StereoPipeline:
         # the ticket keeps the tensor alive until the frame has been collected, so the caching allocator cannot hand its memory to
         # someone else while the slot's stream still reads it (record_stream() on a library-owned stream would leave the allocator
         # holding a stream handle that the pipe destroys)
-        return self._submit(pipe, slot, frame_dev.data_ptr(), cur.cuda_stream, keep=frame_dev)
+        return self._submit(pipe, slot, frame_dev.data_ptr(), cur.cuda_stream, keep=frame_dev, fps=fps)
 
     # ---- collection ----
     def result(self, ticket: _Ticket | None = None, host: bool = True):
@@ -233,16 +242,18 @@ class StereoPipeline:
         """The [h,w] fp16 depth map (what predict_depth returns) of a collected frame; valid until the slot is reused."""
         return ticket.pipe.dev_depth[ticket.slot]
 
-    def run(self, frames, host: bool = True):
-        """Generator: keeps the pipeline full while iterating `frames`; yields results in order."""
+    def run(self, frames, host: bool = True, fps=None):
+        """Generator: keeps the pipeline full while iterating `frames`; yields results in order.  fps (show_fps=True): a number
+        or a callable returning the current rate, passed to every submit like main.py passes `current_fps` to make_sbs."""
         def submit(f):
+            rate = fps() if callable(fps) else fps
             if not host:
-                return self.submit_device(f)
+                return self.submit_device(f, fps=rate)
             if isinstance(f, torch.Tensor):
                 if f.is_pinned():
-                    return self.submit_pinned(f)      # already in pinned host memory: no staging copy on the host
+                    return self.submit_pinned(f, fps=rate)      # already in pinned host memory: no staging copy on the host
                 f = f.numpy()
-            return self.submit(f)
+            return self.submit(f, fps=rate)
         for f in frames:
             if len(self.pending) == self.n_slots:
                 yield self.result(host=host)

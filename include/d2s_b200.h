@@ -272,7 +272,9 @@ typedef struct d2s_pipe_config {
                                      them as one batch (BASELINE configs 3/5: 8 x 4K), each stream keeps its own DepthStabilizer state */
     int32_t jpeg_quality;         /* D2S_OUT_JPEG: IMWRITE_JPEG_QUALITY (MJPEGStreamer's `quality`, streamer.py:113); 0 -> 90 */
     int32_t jpeg_restart_interval;/* D2S_OUT_JPEG: MCUs (16x16 pixels) per restart interval; 0 -> 4 */
-    int32_t reserved[1];
+    int32_t fps_overlay;          /* 1: make_sbs's `fps=` argument (depth.py:2186, 2226-2227): d2s_pipe_set_fps_text() may give a text that
+                                     overlay_fps (d2s_overlay_fps) draws onto the RGB frame before the warp — after the depth network
+                                     has read the frame, as in the reference, where predict_depth sees the frame without it */
 } d2s_pipe_config;
 /* Host-synchronous (allocates the slots, builds their plans, captures their graphs).  The pipe borrows `engine`: destroy the pipe
  * before the engine. */
@@ -288,6 +290,10 @@ int d2s_pipe_slot_buffers(d2s_pipe_handle p, int slot, void **host_in, void **ho
 int d2s_pipe_submit(d2s_pipe_handle p, int slot, const void *frame, d2s_stream_t frame_ready_on);
 int d2s_pipe_wait(d2s_pipe_handle p, int slot);   /* block until the slot's frame is complete; the slot may then be reused */
 int d2s_pipe_reset(d2s_pipe_handle p);            /* new video: EMA state (and a temporal engine's window) forgotten; host-synchronous */
+/* The text (<= 32 characters, e.g. "FPS: 59.9") drawn onto the frames of the following submits; NULL or "": none.  Needs
+ * d2s_pipe_config.fps_overlay.  The every-10th-call refresh of the reference's text cache (depth.py:2061-2072) is the caller's:
+ * desktop2stereo_b200/overlay.py keeps it. */
+int d2s_pipe_set_fps_text(d2s_pipe_handle p, const char *text);
 int d2s_pipe_set_trace(d2s_pipe_handle p, int on);               /* record per-stage CUDA events on the frames submitted from now on */
 int d2s_pipe_slot_times(d2s_pipe_handle p, int slot, float ms[3]); /* after wait: process | resize+network+post | upsample+warp */
 

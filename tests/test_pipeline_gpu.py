@@ -165,3 +165,39 @@ def test_pipeline_several_streams_per_submit(cuda_device):
             # moves a pixel by < 0.01 px (sub-grey-level); EMA state is per stream (a shared state would differ by whole levels)
             assert np.abs(got[t][s] - want[t]).max() <= 1.0, (s, t)
             assert np.abs(got[t][s] - want[t]).mean() <= 0.05
+
+
+@pytest.mark.parametrize("ema", [True, False], ids=["ema", "no_ema"])
+def test_pipeline_fps_overlay_equals_make_sbs(cuda_device, ema):
+    """show_fps: the pipe draws overlay_fps between the network and the warp, like make_sbs(fps=...) (depth.py:2226-2227) — same
+    frames bit for bit over 23 calls, so the every-10th-call text refresh (depth.py:2061-2072) is crossed twice; fps=None frames
+    carry no overlay."""
+    from desktop2stereo_b200 import depth, overlay
+    from desktop2stereo_b200.pipeline import StereoPipeline
+    depth.init(make_hf_model("Small", 5, TINY), device=cuda_device, depth_resolution=126)
+    frames = _frames(23)
+    rates = [None if i in (4, 17) else 30.0 + 1.7 * i for i in range(23)]
+    eng = depth.model_wraper.model
+    eng.set_policy("throughput")
+    depth.depth_stabilizer.reset(); overlay.reset_cache()
+    want = []
+    for f, r in zip(frames, rates):
+        rgb = depth.process(f, f.shape[0])
+        d = depth.predict_depth(rgb, use_temporal_smooth=ema)
+        want.append(depth.make_sbs(rgb, d, display_mode="Full-SBS", fps=r).copy())
+    eng.set_policy("latency")
+    overlay.reset_cache()
+    pipe = StereoPipeline(depth_slots=3, display_mode="Full-SBS", use_temporal_smooth=ema, show_fps=True)
+    it = iter(rates)
+    got = [r.copy() for r in pipe.run(iter(frames), fps=lambda: next(it))]
+    pipe.close()
+    assert any(not np.array_equal(want[0], want[10]) for _ in [0])
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), f"frame {i}"
+    # the overlay is really there: frame 4 (fps=None) differs from what fps would have drawn
+    plain = StereoPipeline(depth_slots=3, display_mode="Full-SBS", use_temporal_smooth=ema)
+    ref = [r.copy() for r in plain.run(iter(frames))]
+    plain.close()
+    assert np.array_equal(ref[4], got[4]) and not np.array_equal(ref[5], got[5])
+    with pytest.raises(ValueError):
+        StereoPipeline(depth_slots=1).submit(frames[0], fps=60.0)
