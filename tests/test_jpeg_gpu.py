@@ -104,3 +104,14 @@ def test_pipeline_jpeg_output(cuda_device):
     got2 = [[bytes(x) for x in r] for r in pj.run(iter(pairs))]
     p8.close(); pj.close()
     assert got2 == want2
+
+
+def test_jpeg_matches_committed_golden(cuda_device):
+    """the recorded cv2.imencode streams (tests/golden/jpeg.npz), independent of the cv2 build on this box"""
+    import os
+    from oracle.gen_golden_jpeg import CASES
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jpeg.npz"))
+    for name, h, w, content, q, ri in CASES:
+        if ri == 0:
+            continue                                    # the device encoder always writes restart intervals
+        assert _encode(cuda_device, g[name + "/rgb"], q, ri) == g[name + "/jpeg"].tobytes(), name

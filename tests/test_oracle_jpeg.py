@@ -41,3 +41,4 @@ def test_restart_markers_do_not_change_pixels():
     a = oj.decode(oj.encode_cv2(img, 90, 0))
     b = oj.decode(oj.encode_oracle(img, 90, 4))
     assert np.array_equal(a, b)
+
