@@ -195,6 +195,48 @@ WORKLOADS = {
 # ---------------------------------------------------------------------------------------------------------------------
 # the product arm
 # ---------------------------------------------------------------------------------------------------------------------
+class Watchdog:
+    """bench.py must end with its JSON line.  If no timed region completes for `limit` seconds (a whole default run takes ~90 s),
+    something is stuck: in a block AFTER the headline has been measured, rank 0 prints the line it has — the stalled block named
+    in "aborted" — and every rank leaves with status 0; before that, the ranks leave with status 3 instead of waiting ten
+    minutes for the NCCL watchdog."""
+
+    def __init__(self):
+        self.t = time.monotonic()
+        self.phase, self.optional, self.finalize, self.fd, self.rank, self.done, self.disabled = "setup", False, None, 1, 0, False, False
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def beat(self):
+        self.t = time.monotonic()
+
+    def enter(self, phase, optional):
+        self.phase, self.optional = phase, optional
+        self.beat()
+
+    def _run(self):
+        while True:
+            time.sleep(5)
+            limit = 240 if self.optional else 600
+            if self.disabled or time.monotonic() - self.t <= limit:
+                continue
+            msg = f"no timed region completed for {limit} s in block '{self.phase}'"
+            os.write(2, f"[bench watchdog] rank {self.rank}: {msg}\n".encode())
+            if self.done:
+                os._exit(0)
+            if self.optional and self.finalize is not None:
+                if self.rank == 0:
+                    try:
+                        os.write(self.fd, (json.dumps(self.finalize(aborted=msg)) + "\n").encode())
+                    except Exception as exc:      # noqa: BLE001 - nothing else can be done here
+                        os.write(2, f"[bench watchdog] could not finalize the line: {exc!r}\n".encode())
+                        os._exit(3)
+                os._exit(0)
+            os._exit(3)
+
+
+WATCHDOG = None
+
+
 class Bench:
     def __init__(self, args):
         import torch
@@ -236,6 +278,8 @@ class Bench:
         ms = torch.tensor([s.elapsed_time(e)], device=self.dev)
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        if WATCHDOG is not None:
+            WATCHDOG.beat()
         return ms.item()
 
     def timed(self, fn, steps, min_s=1.0, max_repeats=400):
@@ -399,13 +443,15 @@ def main():
     ap.add_argument("--workload", default="base1080", choices=["base1080", "vda1080"],
                     help="base1080 is the headline (configs[1], with the large4k block); vda1080 (configs[3]) is an extra measurement")
     args = ap.parse_args()
-    if args.impl != "b200":
-        return run_reference(args)
-    if args.workload == "vda1080":
-        return run_vda1080(args)
+    if args.impl != "b200" or args.workload == "vda1080":
+        if WATCHDOG is not None:
+            WATCHDOG.disabled = True          # the reference arm's steps are CPU work of unknown length; nothing there can stall on a GPU
+        return run_reference(args) if args.impl != "b200" else run_vda1080(args)
 
     import numpy as np
     B = Bench(args)
+    if WATCHDOG is not None:
+        WATCHDOG.enter("headline (configs[1])", False)
     torch, dev, world, rank = B.torch, B.dev, B.world, B.rank
     from desktop2stereo_b200 import _lib, depth
     from desktop2stereo_b200.stereo import make_sbs_core
@@ -538,10 +584,52 @@ def main():
     engine.close()
     torch.cuda.empty_cache()
 
+    def finalize(aborted=None):
+        """compact copies inside the keys the driver's parser keeps (e2e / roofline / cpu_baseline), and a summary as the LAST key so
+        the tail of the line carries the 1080p and the 4K numbers side by side.  Also what the watchdog prints if a later block stalls."""
+        if aborted:
+            line["aborted"] = aborted
+        l4 = line.get("large4k")
+        line["e2e"]["legs"] = {"e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"], "serial_ms_per_frame_device": ms_serial / n_serial, "serial_ms_per_frame_e2e": ms_serial_e2e / n_serial}
+        line["roofline"]["others"] = {"gemm_m778_alone_tensor_frac_of_burst": roofline["isolated"]["frac"], "warp_1080p_hbm_frac": roofline_warp["frac"], "frame_graph_tensor_frac_in_flight": roofline_net["frac"],
+                                      "frame_graph_tensor_frac_alone": roofline_net["isolated"]["frac"]}
+        if l4:
+            line["e2e"]["legs"].update({"large4k_value": l4["value"], "large4k_e2e_fp32": l4["e2e"]["value"], "large4k_e2e_u8": l4["e2e_u8"]["value"], "large4k_e2e_nv12": l4["e2e_nv12"]["value"]})
+            line["roofline"]["others"].update({"warp_4k_hbm_frac": l4["roofline_warp"]["frac"], "gemm_m6224_tensor_frac": l4["roofline"]["frac"],
+                                               "large4k_step_graph_tensor_frac": l4["roofline_net"]["frac"]})
+            if "config5" in l4 and "value" in l4["config5"]:
+                line["e2e"]["legs"].update({"config5_value": l4["config5"]["value"], "config5_e2e_fp32": l4["config5"]["e2e"], "config5_e2e_u8": l4["config5"]["e2e_u8"]})
+        if "cpu_baseline" in line and "cpu_baseline_1thread" in line:
+            line["cpu_baseline"]["one_thread"] = line["cpu_baseline_1thread"]["value"]
+            if l4 and "cpu_baseline" in l4:
+                line["cpu_baseline"]["large4k_all_cores"] = l4["cpu_baseline"]["value"]
+            if "config1" in line:
+                line["cpu_baseline"]["config1_one_thread"] = line["config1"]["cpu_1thread"]["value"]
+            if "reference_cuda" in line:
+                line["cpu_baseline"]["reference_torch_cuda_same_gpu"] = line["reference_cuda"]["value"]
+        if "vda1080" in line:
+            line["e2e"]["legs"].update({"vda1080_value": line["vda1080"]["value"], "vda1080_e2e_fp32": line["vda1080"]["e2e"]})
+        line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"],
+                                        "e2e_jpeg_noise": legs["e2e_jpeg"]["fps"], "e2e_jpeg_desktop": legs["e2e_jpeg_desktop"]["fps"]},
+                           "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"], "e2e_nv12": l4["e2e_nv12"]["value"],
+                                        "e2e_jpeg_desktop": l4["e2e_jpeg_desktop"]["value"]} if l4 else None),
+                           "vda1080": ({"value": line["vda1080"]["value"], "e2e_fp32": line["vda1080"]["e2e"]} if "vda1080" in line else None),
+                           "reference_cuda_base1080": line.get("reference_cuda", {}).get("value"), "unit": "frames/s", "n_gpus": world}
+        return line
+
+    # the headline is measured: from here on a stalled block costs that block, not the line
+    if WATCHDOG is not None:
+        WATCHDOG.finalize = finalize
     # ================= the 4K half of the metric: configs[2] per GPU, configs[4] across GPUs =================
     if not args.no_large4k:
+        if WATCHDOG is not None:
+            WATCHDOG.enter("large4k (configs[2], configs[4])", True)
         line["large4k"] = large4k_block(B, args)
+        if WATCHDOG is not None:
+            WATCHDOG.enter("vda1080 (configs[3])", True)
         line["vda1080"] = vda1080_block(B, args)
+    if WATCHDOG is not None:
+        WATCHDOG.enter("reference arms / wrap-up", True)
     # ================= reference arms measured in the same run (rank 0, N = 1) =================
     if rank == 0 and world == 1 and not args.no_reference_cuda:
         rfps, rdt = cuda_reference_fps(30, 5, dev)
@@ -557,34 +645,12 @@ def main():
         line["cpu_baseline_1thread"] = {"value": c1, "unit": "frames/s", "cores": 1, "kind": "port",
                                         "sample": f"2 frames after 1 warm-up ({c1dt:.1f} s); torch.set_num_threads(1) is what the reference ships (depth.py:19)"}
         line["config1"] = config1_block(B, threads)
-    # compact copies inside the keys the driver's parser keeps (e2e / roofline / cpu_baseline), and a summary as the LAST key so the
-    # tail of the line carries the 1080p and the 4K numbers side by side
-    l4 = line.get("large4k")
-    line["e2e"]["legs"] = {"e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"], "serial_ms_per_frame_device": ms_serial / n_serial, "serial_ms_per_frame_e2e": ms_serial_e2e / n_serial}
-    line["roofline"]["others"] = {"gemm_m778_alone_tensor_frac_of_burst": roofline["isolated"]["frac"], "warp_1080p_hbm_frac": roofline_warp["frac"], "frame_graph_tensor_frac_in_flight": roofline_net["frac"],
-                                  "frame_graph_tensor_frac_alone": roofline_net["isolated"]["frac"]}
-    if l4:
-        line["e2e"]["legs"].update({"large4k_value": l4["value"], "large4k_e2e_fp32": l4["e2e"]["value"], "large4k_e2e_u8": l4["e2e_u8"]["value"], "large4k_e2e_nv12": l4["e2e_nv12"]["value"]})
-        line["roofline"]["others"].update({"warp_4k_hbm_frac": l4["roofline_warp"]["frac"], "gemm_m6224_tensor_frac": l4["roofline"]["frac"],
-                                           "large4k_step_graph_tensor_frac": l4["roofline_net"]["frac"]})
-        if "config5" in l4 and "value" in l4["config5"]:
-            line["e2e"]["legs"].update({"config5_value": l4["config5"]["value"], "config5_e2e_fp32": l4["config5"]["e2e"], "config5_e2e_u8": l4["config5"]["e2e_u8"]})
-    if "cpu_baseline" in line:
-        line["cpu_baseline"]["one_thread"] = line["cpu_baseline_1thread"]["value"]
-        if l4 and "cpu_baseline" in l4:
-            line["cpu_baseline"]["large4k_all_cores"] = l4["cpu_baseline"]["value"]
-        line["cpu_baseline"]["config1_one_thread"] = line["config1"]["cpu_1thread"]["value"]
-        if "reference_cuda" in line:
-            line["cpu_baseline"]["reference_torch_cuda_same_gpu"] = line["reference_cuda"]["value"]
-    if "vda1080" in line:
-        line["e2e"]["legs"].update({"vda1080_value": line["vda1080"]["value"], "vda1080_e2e_fp32": line["vda1080"]["e2e"]})
-    line["summary"] = {"base1080": {"value": line["value"], "e2e_fp32": line["e2e"]["value"], "e2e_u8": e2e8["fps"], "e2e_nv12": e2en["fps"],
-                                    "e2e_jpeg_noise": legs["e2e_jpeg"]["fps"], "e2e_jpeg_desktop": legs["e2e_jpeg_desktop"]["fps"]},
-                       "large4k": ({"value": l4["value"], "e2e_fp32": l4["e2e"]["value"], "e2e_u8": l4["e2e_u8"]["value"], "e2e_nv12": l4["e2e_nv12"]["value"],
-                                    "e2e_jpeg_desktop": l4["e2e_jpeg_desktop"]["value"]} if l4 else None),
-                       "vda1080": ({"value": line["vda1080"]["value"], "e2e_fp32": line["vda1080"]["e2e"]} if "vda1080" in line else None),
-                       "reference_cuda_base1080": line.get("reference_cuda", {}).get("value"), "unit": "frames/s", "n_gpus": world}
-    if rank == 0:
+    finalize()
+    if WATCHDOG is not None:        # the line goes out before the process group is torn down (a teardown that stalls cannot lose it)
+        WATCHDOG.done = True
+        if rank == 0:
+            os.write(WATCHDOG.fd, (json.dumps(line) + "\n").encode())
+    elif rank == 0:
         print(json.dumps(line))
     if world > 1:
         B.dist.destroy_process_group()
@@ -1021,6 +1087,10 @@ def _main_with_clean_stdout():
     sys.stdout.flush()
     real = os.dup(1)
     os.dup2(2, 1)
+    global WATCHDOG
+    WATCHDOG = Watchdog()
+    WATCHDOG.fd = real
+    WATCHDOG.rank = int(os.environ.get("RANK", "0"))
     buf = io.StringIO()
     old = sys.stdout
     sys.stdout = buf
