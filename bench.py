@@ -624,7 +624,7 @@ def main():
     if not args.no_large4k:
         if WATCHDOG is not None:
             WATCHDOG.enter("large4k (configs[2], configs[4])", True)
-        line["large4k"] = large4k_block(B, args)
+        line["large4k"] = large4k_block(B, args, publish=lambda d: line.__setitem__("large4k", d))
         if WATCHDOG is not None:
             WATCHDOG.enter("vda1080 (configs[3])", True)
         line["vda1080"] = vda1080_block(B, args)
@@ -657,7 +657,7 @@ def main():
     return 0
 
 
-def large4k_block(B, args):
+def large4k_block(B, args, publish=None):
     """configs[2] per GPU: DA-V2-Large, 8 concurrent 4K streams, one frame of each per step, batched through the network (6224 token
     rows) -> 8 Full-SBS frames.  Under torchrun also configs[4]: 8 streams x 8 frames in total, stream s -> rank s mod G."""
     torch, dev, world, rank = B.torch, B.dev, B.world, B.rank
@@ -700,7 +700,11 @@ def large4k_block(B, args):
                             "achieved": net_tf, "peak": B.peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": net_tf / B.peaks["bf16_tflops_sustained"],
                             "gflop_per_step": gflop, "duration_ms": step_ms},
            "roofline_warp": warp_roofline_4k(B, traffic)}
+    if publish is not None:      # the per-GPU block is complete: what follows (configs[4]) adds to it, and cannot take it away if it stalls
+        publish(out)
     if world > 1:      # configs[4]: 8 streams in total, stream s -> rank s % G, 8 frames per stream
+        if WATCHDOG is not None:
+            WATCHDOG.enter("config5 (configs[4])", True)
         from desktop2stereo_b200.sharding import streams_for_rank
         mine = streams_for_rank(8, rank, world)
         sl = len(mine)
