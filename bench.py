@@ -201,6 +201,9 @@ class Watchdog:
     in "aborted" — and every rank leaves with status 0; before that, the ranks leave with status 3 instead of waiting ten
     minutes for the NCCL watchdog."""
 
+    LIMITS = (240.0, 600.0)       # seconds without a completed timed region: in a block after the headline / before it
+    POLL = 5.0
+
     def __init__(self):
         self.t = time.monotonic()
         self.phase, self.optional, self.finalize, self.fd, self.rank, self.done, self.disabled = "setup", False, None, 1, 0, False, False
@@ -215,11 +218,11 @@ class Watchdog:
 
     def _run(self):
         while True:
-            time.sleep(5)
-            limit = 240 if self.optional else 600
+            time.sleep(self.POLL)
+            limit = self.LIMITS[0] if self.optional else self.LIMITS[1]
             if self.disabled or time.monotonic() - self.t <= limit:
                 continue
-            msg = f"no timed region completed for {limit} s in block '{self.phase}'"
+            msg = f"no timed region completed for {limit:g} s in block '{self.phase}'"
             os.write(2, f"[bench watchdog] rank {self.rank}: {msg}\n".encode())
             if self.done:
                 os._exit(0)
