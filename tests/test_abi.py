@@ -41,3 +41,20 @@ def test_error_convention_without_gpu():
     assert rc != 0 and b"d2s_sbs_out_shape" in L.d2s_last_error()
     assert L.d2s_make_sbs(None, None) != 0
     assert b"sm_100a" in L.d2s_version()
+
+
+def test_jpeg_sizing_calls_without_gpu():
+    """d2s_jpeg_workspace_bytes / d2s_jpeg_max_bytes are host arithmetic: geometry, monotonicity and the error convention"""
+    L = _lib.lib()
+    # 1080p Full-SBS, 4 MCUs per restart interval: 240 x 68 MCUs -> 4080 intervals
+    ws = L.d2s_jpeg_workspace_bytes(1080, 3840, 4)
+    coef = 240 * 68 * 6 * 64 * 2
+    slots = 4080 * (4 * 6 * 416 + 16)
+    assert ws >= coef + slots + 2 * 4080 * 4 and ws < coef + slots + (1 << 20)
+    assert L.d2s_jpeg_max_bytes(1080, 3840, 4) >= 1080 * 3840 * 3          # can never overflow: above the raw frame
+    assert L.d2s_jpeg_workspace_bytes(2160, 7680, 4) > ws
+    for bad in ((1081, 3840, 4), (1080, 3841, 4), (1080, 3840, 0), (1080, 3840, 70000), (0, 0, 4)):
+        assert L.d2s_jpeg_workspace_bytes(*bad) == 0 and L.d2s_jpeg_max_bytes(*bad) == 0
+        assert b"d2s_jpeg" in L.d2s_last_error()
+    assert L.d2s_jpeg_encode(None, 0, 16, 16, 90, 1, None, 0, None, None, 0, None) != 0
+    assert L.d2s_pipe_set_fps_text(None, b"FPS: 60.0") != 0
