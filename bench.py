@@ -61,14 +61,36 @@ def model_flops(cfg, Hm, Wm):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line): NVML polled at 10 Hz from a
+    thread of this process (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints, without
+    spawning a process per leg); `nvidia-smi -lms 100` is the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.nv, self.samples = index, None, [], None, []
+
+    def _nvml_handle(self, nv):
+        try:        # by PCI address, so a CUDA_VISIBLE_DEVICES remap cannot point at the wrong board
+            import torch
+            pr = torch.cuda.get_device_properties(self.index)
+            return nv.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:      # noqa: BLE001
+            return nv.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = self._nvml_handle(nv)
+            nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            self.nv, self._stop = nv, threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:      # noqa: BLE001 - any NVML problem: the nvidia-smi path below
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,31 +98,52 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        while not self._stop.is_set():
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     [n for n, b in zip(self.NAMES, bits) if r & b]))
+            except Exception:      # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+        if self.nv is not None:
+            time.sleep(0.15)
+            self._stop.set()
+            self.thread.join(timeout=2.0)
+            for a, b, rs in self.samples:
+                sm.append(float(a)); mx.append(float(b)); reasons.update(rs)
+            source = "nvml"
+        elif self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(self.NAMES, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            source = "nvidia-smi"
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": source}
 
 
 
