@@ -238,6 +238,12 @@ WORKLOADS = {
 # ---------------------------------------------------------------------------------------------------------------------
 # the product arm
 # ---------------------------------------------------------------------------------------------------------------------
+def write_all(fd, text):
+    data = text.encode()
+    while data:
+        data = data[os.write(fd, data):]
+
+
 class Watchdog:
     """bench.py must end with its JSON line.  If no timed region completes for `limit` seconds (a whole default run takes ~90 s),
     something is stuck: in a block AFTER the headline has been measured, rank 0 prints the line it has — the stalled block named
@@ -272,7 +278,7 @@ class Watchdog:
             if self.optional and self.finalize is not None:
                 if self.rank == 0:
                     try:
-                        os.write(self.fd, (json.dumps(self.finalize(aborted=msg)) + "\n").encode())
+                        write_all(self.fd, json.dumps(self.finalize(aborted=msg)) + "\n")
                     except Exception as exc:      # noqa: BLE001 - nothing else can be done here
                         os.write(2, f"[bench watchdog] could not finalize the line: {exc!r}\n".encode())
                         os._exit(3)
@@ -695,7 +701,7 @@ def main():
     if WATCHDOG is not None:        # the line goes out before the process group is torn down (a teardown that stalls cannot lose it)
         WATCHDOG.done = True
         if rank == 0:
-            os.write(WATCHDOG.fd, (json.dumps(line) + "\n").encode())
+            write_all(WATCHDOG.fd, json.dumps(line) + "\n")
     elif rank == 0:
         print(json.dumps(line))
     if world > 1:
