@@ -132,3 +132,17 @@ def test_install_end_to_end_through_patched_names(cuda_device):
     assert sbs.shape == (90, 160, 3) and sbs.dtype == np.float32 and np.isfinite(sbs).all()
     x = torch.zeros(1, 3, 70, 126, device=cuda_device)
     assert tuple(m.model_wraper(x).shape) == (1, 70, 126)
+
+
+def test_jpeg_frame_parsing_host_logic():
+    """pipeline._jpeg_streams: d2s_pipe_jpeg_frame buffers (u32 size, 12 reserved bytes, stream) -> the streams they hold"""
+    import numpy as np
+    from desktop2stereo_b200.pipeline import _jpeg_streams
+    buf = np.zeros((2, 64), np.uint8)
+    for b, payload in enumerate((b"\xff\xd8abc\xff\xd9", b"\xff\xd8\xff\xd9")):
+        buf[b, :4] = np.frombuffer(np.uint32(len(payload)).tobytes(), np.uint8)
+        buf[b, 16:16 + len(payload)] = np.frombuffer(payload, np.uint8)
+    one = _jpeg_streams(buf[0], 1)
+    assert bytes(one) == b"\xff\xd8abc\xff\xd9"
+    two = _jpeg_streams(buf, 2)
+    assert [bytes(x) for x in two] == [b"\xff\xd8abc\xff\xd9", b"\xff\xd8\xff\xd9"]
